@@ -1,0 +1,451 @@
+"""NumPy/SciPy restatement of GeoBO's joint-inversion hot path.  TEST INFRASTRUCTURE ONLY.
+
+See ``oracle/__init__.py`` for who may import this.  Every function cites the
+reference lines it restates (paths relative to the reference repo).  Two paths:
+
+* ``cubing_literal`` -- the algorithm exactly as the reference runs it: dense
+  ``D2`` (N x N), dense ``kcov`` (3N x 3N), dense zero-padded ``Asens3`` (M x 3N),
+  full posterior covariance.  Needs ~30 N^2 x 8 B; small cubes only.
+* ``cubing_lean``    -- the same arithmetic with the structure exploited
+  (``Asens3`` is block-diagonal, ``kcov`` symmetric, only diag(cov) is used):
+  ``Pt = Asens3 . kcov`` assembled block by block in row panels, ``AkA = Asens3 . Pt^T``,
+  ``var = amp - colsumsq(L^-1 Pt)``.  Scales to the benchmark cubes; this is the
+  CPU baseline ``bench.py`` times.
+
+Parity status: pinned against the reference's committed result cubes and live
+reference runs (``tests/test_oracle_golden.py``).
+"""
+import json
+import math
+import time
+
+import numpy as np
+from scipy.linalg import cholesky, solve_triangular
+
+ALONG_WAY = 1e6  # sensormodel.py:64 ("aLongWay")
+
+
+# --------------------------------------------------------------------------- config
+class Config(dict):
+    """Settings + derived constants, as ``geobo/config_loader.py:33-59`` injects them as globals."""
+
+    __getattr__ = dict.__getitem__
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def make_config(cfg):
+    """``cfg``: dict of YAML keys (or JSON string).  Adds the derived names of config_loader.py:41-59."""
+    if isinstance(cfg, (str, bytes)):
+        cfg = json.loads(cfg)
+    c = Config(cfg)
+    c.xLcube = c.xmax - c.xmin                         # config_loader.py:41
+    c.yLcube = c.ymax - c.ymin                         # :42
+    c.zmin = c.zmax - c.zLcube                         # :44
+    c.magneticField = np.asarray([c.XMAG, c.YMAG, c.ZMAG]) * 1e-3   # :46
+    c.c_MILLIGALS_UNITS = c.c_G * c.c_SI_TO_MILLIGALS * c.c_GCM3_TO_SI  # :53
+    c.xvoxsize = c.xLcube / c.xNcube * 1.0             # :56-58
+    c.yvoxsize = c.yLcube / c.yNcube * 1.0
+    c.zvoxsize = c.zLcube / c.zNcube * 1.0
+    c.Nsensor = c.xNcube * c.yNcube                    # :59
+    return c
+
+
+def load_yaml(path, **overrides):
+    import yaml
+    with open(path) as f:
+        cfg = yaml.safe_load(f)
+    cfg.update(overrides)
+    return make_config(cfg)
+
+
+# --------------------------------------------------------------------------- kernels.py
+def grid_points(Lpix, pixscale):
+    """kernels.py:27-42 -- points ((ix+1)sx, (iy+1)sy, (iz+1)sz), row = (iy*xN+ix)*zN+iz."""
+    xr = np.arange(1, Lpix[0] + 1) * pixscale[0]
+    yr = np.arange(1, Lpix[1] + 1) * pixscale[1]
+    zr = np.arange(1, Lpix[2] + 1) * pixscale[2]
+    xg, yg, zg = np.meshgrid(xr, yr, zr)  # default 'xy' indexing -> shape (yN, xN, zN)
+    return np.stack([xg.ravel(), yg.ravel(), zg.ravel()], axis=1)
+
+
+def sqdist(points, rows=None):
+    """kernels.py:45-61 -- D2[i,j] = sum_d (p[j,d]-p[i,d])^2, summed in dimension order starting from 0."""
+    p = np.asarray(points, dtype=float)
+    q = p if rows is None else p[rows]
+    acc = 0  # np.sum(generator) == builtin sum: starts from int 0, adds d = 0, 1, 2 in order
+    for d in range(p.shape[1]):
+        delta = p[:, d][None, :] - q[:, d][:, None]
+        acc = acc + delta ** 2
+    return acc
+
+
+def k_exp(D2, g):                       # kernels.py:81-88
+    return np.exp(-0.5 * D2 / g ** 2)
+
+
+def k_exp2(D2, l1, l2):                 # kernels.py:90-99
+    return np.sqrt(2.0 * l1 * l2 / (l1 ** 2 + l2 ** 2)) * np.exp(-D2 / (l1 ** 2 + l2 ** 2))
+
+
+def k_sparse(D2, g):                    # kernels.py:101-114
+    d = np.sqrt(D2)
+    res = np.zeros_like(d)
+    m = d < g
+    dm = d[m]
+    res[m] = (2 + np.cos(2 * np.pi * dm / g)) / 3.0 * (1 - dm / g) + 1 / (2.0 * np.pi) * np.sin(2 * np.pi * dm / g)
+    res[res < 0.0] = 0.0
+    return res
+
+
+def k_sparse2(D2, l1, l2):              # kernels.py:116-138 (Q3: cosine sits inside the sine in branch A)
+    d = np.sqrt(D2)
+    if l1 == l2:
+        l2 = l2 + 1e-3 * l2
+    lmean = np.mean([l1, l2])
+    lmin = np.min([l1, l2])
+    lmax = np.max([l1, l2])
+    res = np.zeros_like(d)
+    mA = d <= abs(l2 - l1) / 2.0
+    res[mA] = 2.0 / (3 * np.sqrt(l1 * l2)) * (
+        lmin + 1 / np.pi * lmax ** 3 / (lmax ** 2 - lmin ** 2)
+        * np.sin(np.pi * lmin / lmax * np.cos(2 * np.pi * d[mA] / lmax)))
+    mB = (d >= abs(l2 - l1) / 2.0) & (d <= (l1 + l2) / 2.0)   # assigned second: wins ties with A
+    dB = d[mB]
+    res[mB] = 2.0 / (3 * np.sqrt(l1 * l2)) * (
+        lmean - dB
+        + l1 ** 3 * np.sin(np.pi * (l2 - 2.0 * dB) / l1) / (2 * np.pi * (l1 ** 2 - l2 ** 2))
+        - l2 ** 3 * np.sin(np.pi * (l1 - 2.0 * dB) / l2) / (2 * np.pi * (l1 ** 2 - l2 ** 2)))
+    res[res < 0.0] = 0.0
+    return res
+
+
+def k_matern32(D2, g):                  # kernels.py:140-146
+    nu = np.sqrt(3) * np.sqrt(D2) / g
+    return (1 + nu) * np.exp(-nu)
+
+
+def k_matern32_2(D2, l1, l2):           # kernels.py:148-156 (singular for l1 == l2)
+    norm = 2 * np.sqrt(l1 * l2) / (l1 ** 2 - l2 ** 2)
+    return norm * (l1 * np.exp(-np.sqrt(3 * D2) / l1) - l2 * np.exp(-np.sqrt(3 * D2) / l2))
+
+
+_SAME = {"exp": k_exp, "sparse": k_sparse, "matern32": k_matern32}
+_CROSS = {"exp": k_exp2, "sparse": k_sparse2, "matern32": k_matern32_2}
+
+
+def dedup_lengths(params):
+    """kernels.py:174-180, *as coded* (Q1): operates in place on an ndarray; the second test
+    rewrites element 1, not 2, so [L,L,L] -> [L, 1.02 L, L]."""
+    if params[1] == params[0]:
+        params[1] = 1.01 * params[0]
+    if params[2] == params[0]:
+        params[1] = 1.02 * params[0]
+    if params[2] == params[1]:
+        params[2] = 1.01 * params[1]
+    return params
+
+
+def cross_weight(w, r, c):
+    """kernels.py:181-194: w1 density-drill (0,2), w2 magsus-drill (1,2), w3 density-magsus (0,1)."""
+    w1, w2, w3 = w
+    return {(0, 1): w3, (0, 2): w1, (1, 2): w2}[(min(r, c), max(r, c))]
+
+
+def cov_block(D2, params, w, fkernel, r, c):
+    """Block at row-block r, column-block c of kernels.py:183-195 (column strip c, vstack slot r):
+    same-property kernel on the diagonal, else w * cross(params[[c, r]])."""
+    if r == c:
+        return _SAME[fkernel](D2, params[c])
+    return cross_weight(w, r, c) * _CROSS[fkernel](D2, params[c], params[r])
+
+
+def create_cov(D2, gplength, crossweights=(1, 1, 1), fkernel="sparse"):
+    """kernels.py:158-195.  ``np.asarray`` aliases an ndarray argument, so the de-dup mutates the caller's array."""
+    params = dedup_lengths(np.asarray(gplength))
+    w = np.asarray(crossweights)
+    strips = [np.vstack([cov_block(D2, params, w, fkernel, r, c) for r in range(3)]) for c in range(3)]
+    return np.hstack(strips)
+
+
+# --------------------------------------------------------------------------- inversion.py geometry
+def cube_geometry(c):
+    """inversion.py:54-74: edge lattice (3, yN+1, xN+1, zN+1) with depth-positive z; voxel centres (3, N)."""
+    xedge = np.linspace(0, c.xNcube, c.xNcube + 1) * c.xvoxsize
+    yedge = np.linspace(0, c.yNcube, c.yNcube + 1) * c.yvoxsize
+    zedge = np.linspace(0, -c.zNcube, c.zNcube + 1) * c.zvoxsize + c.zmax
+    xE, yE, zE = np.meshgrid(xedge, yedge, zedge)
+    Edges = np.asarray([xE, yE, -zE])
+    xnew = np.arange(c.xvoxsize / 2.0, c.xLcube + c.xvoxsize / 2.0, c.xvoxsize)
+    ynew = np.arange(c.yvoxsize / 2.0, c.yLcube + c.yvoxsize / 2.0, c.yvoxsize)
+    znew = c.zmax - np.arange(c.zvoxsize / 2.0, c.zLcube + c.zvoxsize / 2.0, c.zvoxsize)
+    xxx, yyy, zzz = np.meshgrid(xnew, ynew, znew)
+    voxelpos = np.vstack([xxx.flatten(), yyy.flatten(), zzz.flatten()])
+    return Edges, voxelpos
+
+
+def sensor_grid(c):
+    """run_geobo.py:61-65: sensors over voxel-column centres at height zmax+zoff, row n = iy*xN+ix."""
+    x_s = np.linspace(0.5, c.xNcube - 0.5, c.xNcube) * c.xvoxsize
+    y_s = np.linspace(0.5, c.yNcube - 0.5, c.yNcube) * c.yvoxsize
+    z_s = c.zmax + c.zoff
+    xs, ys, zs = np.meshgrid(x_s, y_s, z_s)
+    return np.asarray([xs.flatten(), ys.flatten(), zs.flatten()]).T
+
+
+# --------------------------------------------------------------------------- sensormodel.py
+def grav_corner(x, y, z):               # sensormodel.py:96-110
+    eps = 1e-9
+    r = np.sqrt(x ** 2 + y ** 2 + z ** 2)
+    return x * np.log(y + r) + y * np.log(x + r) - z * np.arctan((x * y) / (z * r + eps))
+
+
+def magn_corner(x, y, z, bx, by, bz):   # sensormodel.py:113-133
+    r = np.sqrt(x ** 2 + y ** 2 + z ** 2)
+    normB = np.sqrt(bx * bx + by * by + bz * bz)
+    f = 1.0 / normB * ((2.0 * by * bz * np.log(x + r)) + (2.0 * bz * bx * np.log(y + r)) + (2.0 * by * bx * np.log(z + r))
+                       + (bz * bz - by * by) * np.arctan((x * z) / (y * r))
+                       + (bz * bz - bx * bx) * np.arctan((y * z) / (x * r)))
+    return -f
+
+
+def a_sens(c, magneticField, locations, Edges, func, sensors=None):
+    """sensormodel.py:29-93, vectorised over the voxel loops with the loop's own association order
+    (so it is bit-identical to the triple loop); one sensor per outer iteration like the reference.
+    ``sensors``: optional subset of sensor rows (for sampled CPU timing)."""
+    Edges = np.asarray(Edges)
+    xE, yE, zE = Edges[0], Edges[1], Edges[2]
+    bx, by, bz = magneticField[0], magneticField[1], magneticField[2]
+    nsens = c.xNcube * c.yNcube               # hard-wired sensor count, sensormodel.py:54,58 (Q7)
+    rows = range(nsens) if sensors is None else sensors
+    sens = np.zeros((len(rows), c.xNcube * c.yNcube * c.zNcube))
+    for out_row, n in enumerate(rows):
+        x0 = xE - locations[n, 0]
+        y0 = yE - locations[n, 1]
+        z0 = zE - locations[n, 2]
+        x0[0] -= ALONG_WAY                    # :64-68 -- axis 0 is the y-edge index (Q4)
+        y0[0] -= ALONG_WAY
+        x0[-1] += ALONG_WAY
+        y0[-1] += ALONG_WAY
+        with np.errstate(all="ignore"):
+            eZ = grav_corner(x0, y0, z0) if func == "grav" else magn_corner(x0, y0, z0, bx, by, bz)
+        hi, lo = slice(1, None), slice(None, -1)
+        s = -((eZ[hi, hi, hi] - eZ[hi, hi, lo] - eZ[hi, lo, hi] + eZ[hi, lo, lo])
+              - (eZ[lo, hi, hi] - eZ[lo, hi, lo] - eZ[lo, lo, hi] + eZ[lo, lo, lo]))   # :83-84
+        sens[out_row] = s.reshape(-1)
+    if func == "grav":
+        sens = c.c_MILLIGALS_UNITS * sens / c.fcor_grav   # :88-89
+    else:
+        sens = sens / c.fcor_mag                          # :90-91
+    return sens
+
+
+def a_drill(loc, voxelpos):
+    """sensormodel.py:136-153: one-hot rows by exact coordinate equality."""
+    x, y, z = voxelpos[0].flatten(), voxelpos[1].flatten(), voxelpos[2].flatten()
+    sens = np.zeros((loc.shape[1], x.size))
+    for i in range(loc.shape[1]):
+        sel = np.where((x == loc[0, i]) & (y == loc[1, i]) & (z == loc[2, i]))
+        sens[i, sel] = 1
+    return sens
+
+
+# --------------------------------------------------------------------------- inversion.py
+def _normalise(c, grav, mag, drillfield):
+    """inversion.py:208-214 (population std)."""
+    with np.errstate(all="ignore"):
+        gm, gs = grav.mean(), grav.std()
+        mm, ms = mag.mean(), mag.std()
+        dm, ds = (drillfield.mean(), drillfield.std()) if drillfield.size else (np.nan, np.nan)
+        y = np.hstack(((grav - gm) / gs, (mag - mm) / ms, (drillfield - dm) / ds))
+    return y, (gs, ms, ds)
+
+
+def _gp_setup(c, gp_length=None):
+    """inversion.py:46-51 (Q6: xvoxsize for all three properties)."""
+    gl = c.gp_lengthscale * np.asarray([c.xvoxsize, c.xvoxsize, c.xvoxsize]) if gp_length is None \
+        else np.array(gp_length, dtype=float)
+    return gl, np.asarray(c.gp_err, dtype=float), np.asarray(c.gp_coeff, dtype=float), 1.0
+
+
+def _finish(c, mu, var, stds):
+    """inversion.py:237-248."""
+    gs, ms, ds = stds
+    shp = (3, c.yNcube, c.xNcube, c.zNcube)
+    rec, rv = mu.reshape(shp), var.reshape(shp)
+    return (rec[0] * gs, rec[1] * ms, rec[2] * ds, rv[0] * gs ** 2, rv[1] * ms ** 2, rv[2] * ds ** 2)
+
+
+def cubing_literal(c, grav, mag, drillfield, sensor_locations, drilldata0, gp_length=None):
+    """inversion.py:182-248 + predict3 :77-122, dense and literal.  Returns (six cubes, extras)."""
+    Edges, voxelpos = cube_geometry(c)
+    xN, yN, zN = c.xNcube, c.yNcube, c.zNcube
+    xxx, yyy, zzz = (v.reshape(xN, yN, zN) for v in voxelpos)            # run_geobo.py:399-403
+    gl, sig, w, amp = _gp_setup(c, gp_length)
+    y, stds = _normalise(c, grav, mag, drillfield)
+    pts = grid_points((xN, yN, zN), (c.xvoxsize, c.yvoxsize, c.zvoxsize))  # :216
+    D2 = sqdist(pts)                                                       # :217
+    mask = drilldata0 != 0
+    vd = np.vstack([xxx[mask], yyy[mask], zzz[mask]])                      # :219
+    Ag = a_sens(c, c.magneticField * 0.0, sensor_locations, Edges, "grav")  # :223
+    Am = a_sens(c, c.magneticField, sensor_locations, Edges, "magn")        # :224
+    Ad = a_drill(vd, voxelpos)                                              # :225
+    Z = np.zeros_like
+    A3 = np.hstack([np.vstack([Ag, Z(Am), Z(Ad)]), np.vstack([Z(Ag), Am, Z(Ad)]), np.vstack([Z(Ag), Z(Am), Ad])])
+    kcov = amp * create_cov(D2, gl, w, fkernel=c.kernelfunc)               # :92 (mutates gl)
+    yerr = np.hstack((grav * 0.0 + sig[0], mag * 0.0 + sig[1], drillfield * 0.0 + sig[2]))
+    AkA = A3 @ (kcov @ A3.T) + np.diag(yerr ** 2)                          # :96
+    L = cholesky(AkA, lower=True)                                          # :100
+    u = solve_triangular(L, y, lower=True)                                 # :105
+    logl = -0.5 * (u @ u + np.log(np.diag(L) ** 2).sum() + xN * yN * zN * np.log(2 * np.pi))  # :108-110 (Q5)
+    V = solve_triangular(L, A3 @ kcov, lower=True)                         # :114
+    mu = V.T @ u                                                           # :115
+    cov = kcov - V.T @ V                                                   # :117
+    var = np.diag(cov)
+    extras = dict(logl=logl, gl_after=gl, mu=mu, var=var, y=y, A3=A3, kcov=kcov, AkA=AkA, V=V, stds=stds)
+    return _finish(c, mu, var, stds), extras
+
+
+def drill_indices(drilldata0):
+    """Flat voxel indices selected by A_drill given how inversion.py:219 builds ``voxelpos_drill``:
+    boolean mask of ``drilldata0 != 0`` in flat (C) order -- each picks exactly its own voxel."""
+    return np.flatnonzero(np.asarray(drilldata0).ravel() != 0)
+
+
+def pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=2048, timers=None):
+    """Columns ``cols`` (voxel indices i) of Pt = Asens3 . kcov for all three property blocks r.
+
+    Returns array (M, 3, len(cols)):  Pt[(cb, s), r, i] = sum_j A_cb[s, j] * K[(cb, j), (r, i)].
+    """
+    Ns = A_list[0].shape[0]
+    nd = didx.size
+    M = 2 * Ns + nd
+    ncol = len(cols)
+    out = np.zeros((M, 3, ncol))
+    N = pts.shape[0]
+    fk = c.kernelfunc
+    for cb in range(2):
+        A = A_list[cb]
+        for j0 in range(0, N, jchunk):
+            J = np.arange(j0, min(N, j0 + jchunk))
+            t0 = time.perf_counter()
+            # D2[j, i] for j in J (rows), i in cols: same arithmetic as sqdist()
+            acc = 0
+            for d in range(3):
+                delta = pts[cols, d][None, :] - pts[J, d][:, None]
+                acc = acc + delta ** 2
+            blocks = [amp * cov_block(acc, params, w, fk, cb, r) for r in range(3)]  # K[(cb,J),(r,cols)] (symmetric)
+            t1 = time.perf_counter()
+            for r in range(3):
+                out[cb * Ns:(cb + 1) * Ns, r, :] += A[:, J] @ blocks[r]
+            t2 = time.perf_counter()
+            if timers is not None:
+                timers["kernel_eval"] = timers.get("kernel_eval", 0.0) + (t1 - t0)
+                timers["dgemm_proj"] = timers.get("dgemm_proj", 0.0) + (t2 - t1)
+    if nd:
+        acc = 0
+        for d in range(3):
+            delta = pts[cols, d][None, :] - pts[didx, d][:, None]
+            acc = acc + delta ** 2
+        for r in range(3):
+            out[2 * Ns:, r, :] = amp * cov_block(acc, params, w, fk, 2, r)
+    return out
+
+
+def predict_lean(c, A_list, didx, y, gl, sig, w, amp, panel=4096, timers=None):
+    """predict3 (inversion.py:77-122) with block structure; returns mu (3N), var (3N), logl, extras."""
+    xN, yN, zN = c.xNcube, c.yNcube, c.zNcube
+    N = xN * yN * zN
+    Ns = A_list[0].shape[0]
+    nd = didx.size
+    M = 2 * Ns + nd
+    params = dedup_lengths(gl)                         # mutates like kernels.py:174-180
+    pts = grid_points((xN, yN, zN), (c.xvoxsize, c.yvoxsize, c.zvoxsize))
+    Pt = np.empty((M, 3, N))
+    for i0 in range(0, N, panel):
+        cols = np.arange(i0, min(N, i0 + panel))
+        Pt[:, :, i0:i0 + len(cols)] = pt_panel(c, params, w, amp, A_list, didx, pts, cols, timers=timers)
+    t0 = time.perf_counter()
+    AkA = np.empty((M, M))
+    AkA[:Ns] = A_list[0] @ Pt[:, 0, :].T               # rows of Asens3 in block 0 only touch property 0
+    AkA[Ns:2 * Ns] = A_list[1] @ Pt[:, 1, :].T
+    if nd:
+        AkA[2 * Ns:] = Pt[:, 2, didx].T
+    yerr2 = np.hstack((np.full(Ns, sig[0] ** 2), np.full(Ns, sig[1] ** 2), np.full(nd, sig[2] ** 2)))
+    AkA[np.diag_indices(M)] += yerr2
+    t1 = time.perf_counter()
+    L = cholesky(AkA, lower=True)
+    t2 = time.perf_counter()
+    u = solve_triangular(L, y, lower=True)
+    logl = -0.5 * (u @ u + np.log(np.diag(L) ** 2).sum() + N * np.log(2 * np.pi))
+    Pt2 = Pt.reshape(M, 3 * N)
+    V = solve_triangular(L, Pt2, lower=True, overwrite_b=True, check_finite=False)
+    t3 = time.perf_counter()
+    mu = V.T @ u
+    var = amp - np.einsum("ij,ij->j", V, V)            # diag(kcov) = amp (Q10)
+    t4 = time.perf_counter()
+    if timers is not None:
+        timers.update(aka=t1 - t0, chol=t2 - t1, trsm=t3 - t2, mean_var=t4 - t3)
+    return mu, var, logl, dict(AkA_chol=L, u=u)
+
+
+def cubing_lean(c, grav, mag, drillfield, sensor_locations, drilldata0, gp_length=None, timers=None):
+    """Same result as ``cubing_literal`` (to rounding) without any N x N or 3N x 3N array."""
+    Edges, voxelpos = cube_geometry(c)
+    gl, sig, w, amp = _gp_setup(c, gp_length)
+    y, stds = _normalise(c, grav, mag, drillfield)
+    t0 = time.perf_counter()
+    Ag = a_sens(c, c.magneticField * 0.0, sensor_locations, Edges, "grav")
+    Am = a_sens(c, c.magneticField, sensor_locations, Edges, "magn")
+    if timers is not None:
+        timers["a_sens"] = time.perf_counter() - t0
+    didx = drill_indices(drilldata0)
+    mu, var, logl, ex = predict_lean(c, [Ag, Am], didx, y, gl, sig, w, amp, timers=timers)
+    extras = dict(logl=logl, gl_after=gl, mu=mu, var=var, y=y, stds=stds, A_grav=Ag, A_magn=Am, didx=didx)
+    return _finish(c, mu, var, stds), extras
+
+
+def calc_logl(c, A_list, didx, y, params5):
+    """inversion.py:125-152: negative log marginal likelihood for [amp, length-multiplier, w1, w2, w3]
+    (no N log 2pi term; any failure -> +inf)."""
+    try:
+        amp = params5[0]
+        gl = params5[1] * np.asarray([c.xvoxsize, c.xvoxsize, c.xvoxsize])
+        w = np.asarray(params5[2:])
+        sig = np.asarray(c.gp_err, dtype=float)
+        N = c.xNcube * c.yNcube * c.zNcube
+        Ns = A_list[0].shape[0]
+        nd = didx.size
+        M = 2 * Ns + nd
+        params = dedup_lengths(gl)
+        pts = grid_points((c.xNcube, c.yNcube, c.zNcube), (c.xvoxsize, c.yvoxsize, c.zvoxsize))
+        Pt = pt_panel(c, params, w, amp, A_list, didx, pts, np.arange(N))
+        AkA = np.empty((M, M))
+        AkA[:Ns] = A_list[0] @ Pt[:, 0, :].T
+        AkA[Ns:2 * Ns] = A_list[1] @ Pt[:, 1, :].T
+        if nd:
+            AkA[2 * Ns:] = Pt[:, 2, didx].T
+        AkA[np.diag_indices(M)] += np.hstack((np.full(Ns, sig[0] ** 2), np.full(Ns, sig[1] ** 2), np.full(nd, sig[2] ** 2)))
+        L = cholesky(AkA, lower=True)
+        u = solve_triangular(L, y, lower=True)
+        logl = -0.5 * (u @ u + np.log(np.diag(L) ** 2).sum())
+        if not np.isfinite(logl):
+            raise FloatingPointError
+    except Exception:
+        logl = -np.inf
+    return -logl
+
+
+# --------------------------------------------------------------------------- synthetic truth (bench inputs)
+def cylinders_truth(c, voxelpos):
+    """simcube.py:83-92 ('cylinders'): density/magsus cubes as pure functions of voxel coordinates."""
+    x3, y3, z3 = (v.reshape(c.yNcube, c.xNcube, c.zNcube) for v in voxelpos)
+    rad = c.yLcube / 18.0
+    rc1 = (y3 - c.yLcube / 1.3 - rad) ** 2 + (z3 + c.zLcube / 4 - rad) ** 2
+    rc2 = (y3 - c.yLcube / 4.0 - rad) ** 2 + (z3 + c.zLcube / 4 - rad) ** 2
+    density = x3 * 0.0 + 0.1
+    density[rc2 <= rad ** 2] = 1.0
+    density[rc1 <= rad ** 2] = 1.0
+    density[(x3 < c.xLcube / 5.0) | (x3 > c.xLcube * 4.0 / 5.0)] = 0.1
+    return density, c.gp_coeff[1] * density
