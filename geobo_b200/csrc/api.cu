@@ -1,0 +1,699 @@
+// C ABI of libgeobo_b200 (see include/geobo_b200.h): context, the geobo.kernels / geobo.sensormodel
+// compatibility entry points, and the device-resident joint inversion (Inversion.cubing / predict3).
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "comm.h"
+
+std::string g_gb_create_error;
+
+// ====================================================================================== context
+extern "C" int gb_version(void) { return 100; }
+
+extern "C" int gb_ctx_create(int device, gb_ctx** out) {
+    if (!out) return gb_fail(nullptr, GB_ERR_ARG, "gb_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return gb_fail(nullptr, GB_ERR_CUDA, "no CUDA device available (%s); geobo_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0) GB_CUDA(nullptr, cudaGetDevice(&device));
+    if (device >= ndev) return gb_fail(nullptr, GB_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    GB_CUDA(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GB_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return gb_fail(nullptr, GB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                       prop.major, prop.minor);
+    gb_ctx* ctx = new gb_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = gemm::init();
+    if (e != cudaSuccess) {
+        int rc = gb_fail(nullptr, GB_ERR_CUDA, "context init: %s", cudaGetErrorString(e));
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return GB_OK;
+}
+
+extern "C" int gb_ctx_destroy(gb_ctx* ctx) {
+    if (!ctx) return GB_OK;
+    cudaSetDevice(ctx->device);
+    comm_destroy(ctx);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GB_OK;
+}
+
+extern "C" const char* gb_last_error(const gb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_gb_create_error.c_str(); }
+
+extern "C" int gb_device_info(gb_ctx* ctx, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor,
+                              uint64_t* free_bytes, uint64_t* total_bytes) {
+    if (!ctx) return GB_ERR_ARG;
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    GB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    if (name && name_len > 0) snprintf(name, name_len, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    size_t f = 0, t = 0;
+    GB_CUDA(ctx, cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return GB_OK;
+}
+
+static int fill_cov_params(gb_ctx* ctx, CovParams& cp, int kernel_id, const double l[3], const double w[3], double amp) {
+    if (kernel_id != GB_KERNEL_SPARSE && kernel_id != GB_KERNEL_EXP && kernel_id != GB_KERNEL_MATERN32)
+        return gb_fail(ctx, GB_ERR_ARG, "unknown kernel id %d", kernel_id);
+    cp.kernel_id = kernel_id;
+    for (int i = 0; i < 3; ++i) { cp.l[i] = l[i]; cp.w[i] = w[i]; }
+    cp.amp = amp;
+    return GB_OK;
+}
+
+// ====================================================================================== geobo/kernels.py
+extern "C" int gb_grid_points(gb_ctx* ctx, const int64_t lpix[3], const double pixscale[3], double* out) {
+    if (!ctx || !lpix || !pixscale || !out) return gb_fail(ctx, GB_ERR_ARG, "gb_grid_points: null argument");
+    const int64_t N = lpix[0] * lpix[1] * lpix[2];
+    if (lpix[0] < 1 || lpix[1] < 1 || lpix[2] < 1 || N > (1LL << 31)) return gb_fail(ctx, GB_ERR_ARG, "gb_grid_points: bad grid");
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> d;
+    GB_CUDA(ctx, d.alloc(3 * N));
+    GB_CUDA(ctx, launch_grid_points(lpix, pixscale, d.p, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(out, d.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+extern "C" int gb_sqdist(gb_ctx* ctx, const double* points, int64_t n, int dim, double* out) {
+    if (!ctx || !points || !out || n < 1 || dim < 1) return gb_fail(ctx, GB_ERR_ARG, "gb_sqdist: bad argument");
+    if (n > 65535) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "gb_sqdist: n=%lld > 65535 (dense n x n output)", (long long)n);
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> p, d;
+    GB_CUDA(ctx, p.alloc(n * dim));
+    GB_CUDA(ctx, d.alloc(n * n));
+    GB_CUDA(ctx, cudaMemcpyAsync(p.p, points, n * dim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, launch_sqdist(p.p, n, dim, d.p, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(out, d.p, n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+extern "C" int gb_create_cov(gb_ctx* ctx, const double* D2, int64_t n, const double gpl[3], const double w[3], int kernel_id,
+                             double* out) {
+    if (!ctx || !D2 || !gpl || !w || !out || n < 1) return gb_fail(ctx, GB_ERR_ARG, "gb_create_cov: bad argument");
+    if (n > 65535) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "gb_create_cov: n=%lld > 65535 (dense 3n x 3n output)", (long long)n);
+    CovParams cp;
+    GB_TRY(fill_cov_params(ctx, cp, kernel_id, gpl, w, 1.0));
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> d2, o;
+    GB_CUDA(ctx, d2.alloc(n * n));
+    GB_CUDA(ctx, o.alloc(9 * n * n));
+    GB_CUDA(ctx, cudaMemcpyAsync(d2.p, D2, n * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, launch_create_cov_dense(cp, d2.p, n, o.p, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(out, o.p, 9 * n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+extern "C" int gb_create_cov_grid(gb_ctx* ctx, const int64_t ncube[3], const double vox[3], const double gpl[3],
+                                  const double w[3], double amp, int kernel_id, double* out, float* ms) {
+    if (!ctx || !ncube || !vox || !gpl || !w) return gb_fail(ctx, GB_ERR_ARG, "gb_create_cov_grid: null argument");
+    const int64_t N = ncube[0] * ncube[1] * ncube[2];
+    if (N < 1 || 3 * N > (1LL << 31) - 1) return gb_fail(ctx, GB_ERR_ARG, "gb_create_cov_grid: bad grid");
+    CovParams cp;
+    GB_TRY(fill_cov_params(ctx, cp, kernel_id, gpl, w, amp));
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> o;
+    GB_CUDA(ctx, o.alloc(9 * N * N));
+    cudaEvent_t e0, e1;
+    GB_CUDA(ctx, cudaEventCreate(&e0));
+    GB_CUDA(ctx, cudaEventCreate(&e1));
+    GB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    GB_CUDA(ctx, launch_create_cov_grid(cp, ncube, vox, o.p, ctx->stream));
+    GB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    if (out) GB_CUDA(ctx, cudaMemcpyAsync(out, o.p, 9 * N * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float t = 0.f;
+    GB_CUDA(ctx, cudaEventElapsedTime(&t, e0, e1));
+    if (ms) *ms = t;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return GB_OK;
+}
+
+extern "C" int gb_cov_function(gb_ctx* ctx, int kernel_id, int cross, const double* D2, int64_t count, double l1, double l2,
+                               double* out) {
+    if (!ctx || !D2 || !out || count < 0) return gb_fail(ctx, GB_ERR_ARG, "gb_cov_function: bad argument");
+    if (kernel_id != GB_KERNEL_SPARSE && kernel_id != GB_KERNEL_EXP && kernel_id != GB_KERNEL_MATERN32)
+        return gb_fail(ctx, GB_ERR_ARG, "unknown kernel id %d", kernel_id);
+    if (count == 0) return GB_OK;
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> d, o;
+    GB_CUDA(ctx, d.alloc(count));
+    GB_CUDA(ctx, o.alloc(count));
+    GB_CUDA(ctx, cudaMemcpyAsync(d.p, D2, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, launch_cov_function(kernel_id, cross, d.p, count, l1, l2, o.p, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(out, o.p, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+// ====================================================================================== geobo/sensormodel.py
+extern "C" int gb_corner_func(gb_ctx* ctx, int kind, const double* x, const double* y, const double* z, int64_t count,
+                              const double B[3], double* out) {
+    if (!ctx || !x || !y || !z || !out || count < 0) return gb_fail(ctx, GB_ERR_ARG, "gb_corner_func: bad argument");
+    if (kind != GB_SENS_GRAV && kind != GB_SENS_MAGN) return gb_fail(ctx, GB_ERR_ARG, "gb_corner_func: unknown func %d", kind);
+    if (kind == GB_SENS_MAGN && !B) return gb_fail(ctx, GB_ERR_ARG, "gb_corner_func: B missing");
+    if (count == 0) return GB_OK;
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> d, o;
+    GB_CUDA(ctx, d.alloc(3 * count));
+    GB_CUDA(ctx, o.alloc(count));
+    GB_CUDA(ctx, cudaMemcpyAsync(d.p, x, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(d.p + count, y, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(d.p + 2 * count, z, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const double zeroB[3] = {0, 0, 0};
+    GB_CUDA(ctx, launch_corner_func(kind, d.p, d.p + count, d.p + 2 * count, count, B ? B : zeroB, o.p, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(out, o.p, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+extern "C" int gb_a_drill(gb_ctx* ctx, const double* loc, int64_t ndrill, const double* voxelpos, int64_t nvox, double* out) {
+    if (!ctx || !voxelpos || !out || ndrill < 0 || nvox < 1 || (ndrill > 0 && !loc)) return gb_fail(ctx, GB_ERR_ARG, "gb_a_drill: bad argument");
+    if (ndrill == 0) return GB_OK;
+    if (ndrill > 65535) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "gb_a_drill: more than 65535 drill rows");
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> l, v, o;
+    GB_CUDA(ctx, l.alloc(3 * ndrill));
+    GB_CUDA(ctx, v.alloc(3 * nvox));
+    GB_CUDA(ctx, o.alloc(ndrill * nvox));
+    GB_CUDA(ctx, cudaMemcpyAsync(l.p, loc, 3 * ndrill * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(v.p, voxelpos, 3 * nvox * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, launch_a_drill(l.p, ndrill, v.p, nvox, o.p, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(out, o.p, ndrill * nvox * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+extern "C" int gb_a_sens(gb_ctx* ctx, int kind, const double B[3], const double* locations, int64_t nsens, const double* edges,
+                         const int64_t ncube[3], double mul, double div, double* out) {
+    if (!ctx || !B || !locations || !edges || !ncube || !out || nsens < 1) return gb_fail(ctx, GB_ERR_ARG, "gb_a_sens: bad argument");
+    if (kind != GB_SENS_GRAV && kind != GB_SENS_MAGN) return gb_fail(ctx, GB_ERR_ARG, "gb_a_sens: unknown func %d", kind);
+    const int64_t N = ncube[0] * ncube[1] * ncube[2];
+    const int64_t nedge = (ncube[0] + 1) * (ncube[1] + 1) * (ncube[2] + 1);
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> e, l, o;
+    GB_CUDA(ctx, e.alloc(3 * nedge));
+    GB_CUDA(ctx, l.alloc(3 * nsens));
+    GB_CUDA(ctx, o.alloc(nsens * N));
+    GB_CUDA(ctx, cudaMemcpyAsync(e.p, edges, 3 * nedge * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(l.p, locations, 3 * nsens * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, launch_a_sens(kind, B, l.p, nsens, e.p, ncube, mul, div, o.p, N, ctx->sm_count, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(out, o.p, nsens * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+// ====================================================================================== geobo/inversion.py
+struct gb_problem {
+    gb_ctx* ctx = nullptr;
+    int64_t n[3] = {0, 0, 0};
+    double vox[3] = {0, 0, 0};
+    int64_t N = 0, Ns = 0, nd = 0, M = 0, Mp = 0;
+    int64_t c0 = 0, c1 = 0, ncol = 0, ncp = 0, ldp = 0;   // local voxel-column shard of Pt
+    int64_t Kp = 0, lda = 0, ext = 0, C0 = 0;
+    std::vector<int64_t> drill;
+    double* A[2] = {nullptr, nullptr};   // [Ns][lda] sensitivities (grav, magn)
+    int* L = nullptr;                    // [Kp] extended-lattice ids
+    int64_t* drill_dev = nullptr;
+    double* tables = nullptr;            // [9][ext]
+    double* Pt = nullptr;                // [Mp][ldp]  Pt = A3 . K, overwritten by V = L^-1 Pt
+    double* tmp = nullptr;               // [128][ldp]
+    double* Bm = nullptr;                // [Mp][Mp]   AkA -> L
+    double* ysol = nullptr;              // [Mp][16]   column 0: y -> u
+    double* ytmp = nullptr;              // [128][16]
+    double* ydev = nullptr;              // [Mp] staged data vector
+    double* linv = nullptr;
+    double* scal = nullptr;              // [0] logdet  [1] u.u
+    int* info = nullptr;
+    double* mu = nullptr;                // [3][ncol]
+    double* var = nullptr;               // [3][ncol]
+    double* y_host_pinned = nullptr;
+    double* out_pinned = nullptr;        // [6*ncol + 4]
+    cudaEvent_t ev[GB_NUM_TIMERS + 1];
+    bool ev_ok = false;
+    double ms[GB_NUM_TIMERS];
+    uint64_t bytes = 0;
+    bool have_data = false;
+};
+
+template <typename T>
+static cudaError_t dev_alloc(gb_problem* p, T** ptr, size_t count, bool zero) {
+    cudaError_t e = cudaMalloc((void**)ptr, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    p->bytes += count * sizeof(T);
+    if (zero) e = cudaMemsetAsync(*ptr, 0, count * sizeof(T), p->ctx->stream);
+    return e;
+}
+
+extern "C" int gb_problem_destroy(gb_problem* p) {
+    if (!p) return GB_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
+                    p->linv, p->scal, p->info, p->mu, p->var};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    if (p->y_host_pinned) cudaFreeHost(p->y_host_pinned);
+    if (p->out_pinned) cudaFreeHost(p->out_pinned);
+    if (p->ev_ok)
+        for (auto& e : p->ev) cudaEventDestroy(e);
+    delete p;
+    return GB_OK;
+}
+
+extern "C" uint64_t gb_problem_device_bytes(gb_problem* p) { return p ? p->bytes : 0; }
+
+extern "C" int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* d, gb_problem** out) {
+    if (!ctx || !d || !out) return gb_fail(ctx, GB_ERR_ARG, "gb_problem_create: null argument");
+    *out = nullptr;
+    const int64_t xN = d->ncube[0], yN = d->ncube[1], zN = d->ncube[2];
+    if (xN < 1 || yN < 1 || zN < 1) return gb_fail(ctx, GB_ERR_ARG, "gb_problem_create: cube dimensions must be >= 1");
+    const int64_t N = xN * yN * zN;
+    if ((2 * xN - 1) * (2 * yN - 1) * (2 * zN - 1) >= (1LL << 31)) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "cube too large for 32-bit lattice ids");
+    if (!d->edges || !d->locations) return gb_fail(ctx, GB_ERR_ARG, "gb_problem_create: edges/locations missing");
+    if (d->nsens != xN * yN)   // sensormodel.py:54,58 hard-wires the sensor count
+        return gb_fail(ctx, GB_ERR_ARG, "nsens=%lld but the forward model is defined for xNcube*yNcube=%lld sensors",
+                       (long long)d->nsens, (long long)(xN * yN));
+    if (d->ndrill < 0 || (d->ndrill > 0 && !d->drill_idx)) return gb_fail(ctx, GB_ERR_ARG, "gb_problem_create: drill_idx missing");
+    for (int64_t i = 0; i < d->ndrill; ++i)
+        if (d->drill_idx[i] < 0 || d->drill_idx[i] >= N) return gb_fail(ctx, GB_ERR_ARG, "drill_idx[%lld] out of range", (long long)i);
+    int64_t c0 = d->col_begin, c1 = d->col_end;
+    if (c0 == 0 && c1 == 0) c1 = N;
+    if (c0 < 0 || c1 > N || c0 >= c1 || (c0 % 16) != 0) return gb_fail(ctx, GB_ERR_ARG, "bad voxel-column shard [%lld, %lld): begin must be a multiple of 16", (long long)c0, (long long)c1);
+    if ((size_t)2 * (xN + 1) * (zN + 1) * 8 > 200 * 1024) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "(xN+1)(zN+1) too large for the A_sens shared-memory planes");
+
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    gb_problem* p = new gb_problem();
+    p->ctx = ctx;
+    for (int i = 0; i < 3; ++i) { p->n[i] = d->ncube[i]; p->vox[i] = d->voxsize[i]; }
+    p->N = N; p->Ns = d->nsens; p->nd = d->ndrill; p->M = 2 * p->Ns + p->nd; p->Mp = round_up(p->M, 128);
+    p->c0 = c0; p->c1 = c1; p->ncol = c1 - c0; p->ncp = round_up(p->ncol, 16); p->ldp = 3 * p->ncp;
+    p->Kp = round_up(N, 16); p->lda = p->Kp + 16;
+    p->ext = (2 * xN - 1) * (2 * yN - 1) * (2 * zN - 1);
+    p->C0 = ((yN - 1) * (2 * xN - 1) + (xN - 1)) * (2 * zN - 1) + (zN - 1);
+    p->drill.assign(d->drill_idx, d->drill_idx + d->ndrill);
+
+#define PCUDA(call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            int rc__ = gb_fail(ctx, e__ == cudaErrorMemoryAllocation ? GB_ERR_NOMEM : GB_ERR_CUDA, "%s:%d %s: %s", \
+                               __FILE__, __LINE__, #call, cudaGetErrorString(e__));                          \
+            cudaGetLastError();                                                                              \
+            gb_problem_destroy(p);                                                                           \
+            return rc__;                                                                                     \
+        }                                                                                                    \
+    } while (0)
+
+    for (auto& e : p->ev) PCUDA(cudaEventCreate(&e));
+    p->ev_ok = true;
+    memset(p->ms, 0, sizeof p->ms);
+    PCUDA(dev_alloc(p, &p->A[0], (size_t)p->Ns * p->lda, true));
+    PCUDA(dev_alloc(p, &p->A[1], (size_t)p->Ns * p->lda, true));
+    PCUDA(dev_alloc(p, &p->L, (size_t)p->Kp, false));
+    PCUDA(dev_alloc(p, &p->drill_dev, (size_t)p->nd + 1, false));
+    PCUDA(dev_alloc(p, &p->tables, (size_t)9 * p->ext, false));
+    PCUDA(dev_alloc(p, &p->Pt, (size_t)p->Mp * p->ldp, true));
+    PCUDA(dev_alloc(p, &p->tmp, (size_t)128 * p->ldp, true));
+    PCUDA(dev_alloc(p, &p->Bm, (size_t)p->Mp * p->Mp, true));
+    PCUDA(dev_alloc(p, &p->ysol, (size_t)p->Mp * 16, true));
+    PCUDA(dev_alloc(p, &p->ytmp, (size_t)128 * 16, true));
+    PCUDA(dev_alloc(p, &p->ydev, (size_t)p->Mp, true));
+    PCUDA(dev_alloc(p, &p->linv, (size_t)p->Mp * 128, false));
+    PCUDA(dev_alloc(p, &p->scal, 4, true));
+    PCUDA(dev_alloc(p, &p->info, 4, true));
+    PCUDA(dev_alloc(p, &p->mu, (size_t)3 * p->ncol, true));
+    PCUDA(dev_alloc(p, &p->var, (size_t)3 * p->ncol, true));
+    PCUDA(cudaMallocHost((void**)&p->y_host_pinned, (size_t)p->Mp * sizeof(double)));
+    PCUDA(cudaMallocHost((void**)&p->out_pinned, (size_t)(6 * p->ncol + 8) * sizeof(double)));
+    if (p->nd) PCUDA(cudaMemcpyAsync(p->drill_dev, p->drill.data(), p->nd * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    PCUDA(launch_lattice_ids(p->n, p->L, p->Kp, ctx->stream));
+
+    // sensitivities (inversion.py:223-224) computed on the device; edges/locations are the only H2D traffic
+    {
+        const int64_t nedge = (xN + 1) * (yN + 1) * (zN + 1);
+        DevBuf<double> e, l;
+        PCUDA(e.alloc(3 * nedge));
+        PCUDA(l.alloc(3 * p->Ns));
+        PCUDA(cudaMemcpyAsync(e.p, d->edges, 3 * nedge * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        PCUDA(cudaMemcpyAsync(l.p, d->locations, 3 * p->Ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        PCUDA(cudaEventRecord(p->ev[0], ctx->stream));
+        const double zeroB[3] = {0.0, 0.0, 0.0};   // inversion.py:223 passes magneticField * 0 for gravity
+        PCUDA(launch_a_sens(GB_SENS_GRAV, zeroB, l.p, p->Ns, e.p, p->n, d->grav_mul, d->grav_div, p->A[0], p->lda, ctx->sm_count, ctx->stream));
+        PCUDA(launch_a_sens(GB_SENS_MAGN, d->magnetic_field, l.p, p->Ns, e.p, p->n, d->magn_mul, d->magn_div, p->A[1], p->lda, ctx->sm_count, ctx->stream));
+        PCUDA(cudaEventRecord(p->ev[1], ctx->stream));
+        PCUDA(cudaStreamSynchronize(ctx->stream));
+        float t = 0.f;
+        PCUDA(cudaEventElapsedTime(&t, p->ev[0], p->ev[1]));
+        p->ms[GB_T_SENS] = t;
+    }
+#undef PCUDA
+    *out = p;
+    return GB_OK;
+}
+
+extern "C" int gb_problem_set_data(gb_problem* p, const double* fs3) {
+    if (!p || !fs3) return GB_ERR_ARG;
+    gb_ctx* ctx = p->ctx;
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(p->y_host_pinned, fs3, p->M * sizeof(double));
+    p->have_data = true;
+    return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------- small kernels of predict
+__global__ void drill_rows_pt_kernel(const double* __restrict__ tables, long ext, long C0, const int* __restrict__ L,
+                                     const int64_t* __restrict__ drill, long c0, long ncol, long ncp, long ldp, long row0,
+                                     double* __restrict__ Pt) {
+    // Pt[(2Ns + d), r*ncp + i] = K[(2, j_d), (r, c0 + i)]  (A_drill is one-hot: a row gather of the covariance)
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int dd = blockIdx.y, r = blockIdx.z;
+    if (i >= ncol) return;
+    const int lj = L[drill[dd]];
+    Pt[(row0 + dd) * ldp + r * ncp + i] = tables[(long)(6 + r) * ext + C0 + (L[c0 + i] - lj)];
+}
+
+__global__ void set_y_kernel(const double* __restrict__ y, long M, long Mp, double* __restrict__ ysol) {
+    const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= Mp) return;
+    ysol[m * 16] = m < M ? y[m] : 0.0;
+}
+
+__global__ void drill_rows_aka_kernel(const double* __restrict__ Pt, long ldp, long ncp, const int64_t* __restrict__ drill,
+                                      long c0, long c1, long row0, long M, double* __restrict__ Bm, long ldb) {
+    // AkA[(2Ns + d), m] = Pt[m, (2, j_d)] restricted to this rank's columns (other ranks contribute through the all-reduce)
+    const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int dd = blockIdx.y;
+    if (m >= M) return;
+    const long j = drill[dd];
+    if (j < c0 || j >= c1) return;
+    Bm[(row0 + dd) * ldb + m] = Pt[m * ldp + 2 * ncp + (j - c0)];
+}
+
+__global__ void add_noise_diag_kernel(double* __restrict__ Bm, long ldb, long Ns, long M, long Mp, double s0, double s1, double s2) {
+    const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= Mp) return;
+    if (m >= M) { Bm[m * ldb + m] = 1.0; return; }          // identity tail of the padded matrix
+    const double s = m < Ns ? s0 : (m < 2 * Ns ? s1 : s2);
+    Bm[m * ldb + m] += s * s;                                // inversion.py:94-96: + diag(yerr**2)
+}
+
+// mu[col] = sum_m V[m,col] u[m];  var[col] = amp - sum_m V[m,col]^2   (inversion.py:115,117 diag only; Q10 diag(K) = amp)
+__global__ void __launch_bounds__(256) mean_var_kernel(const double* __restrict__ V, long ldp, long ncp, long ncol, long M,
+                                                       const double* __restrict__ ysol, double amp, double* __restrict__ mu,
+                                                       double* __restrict__ var) {
+    __shared__ double us[1024];
+    const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;   // over ncp
+    const int r = blockIdx.y;
+    double m0 = 0.0, m1 = 0.0, s0 = 0.0, s1 = 0.0;
+    const bool live = col < ncol;
+    const double* v = V + r * ncp + (live ? col : 0);
+    for (long mb = 0; mb < M; mb += 1024) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < 1024; q += blockDim.x) us[q] = (mb + q < M) ? ysol[(mb + q) * 16] : 0.0;
+        __syncthreads();
+        const int lim = (int)min(1024L, M - mb);
+        int q = 0;
+        for (; q + 1 < lim; q += 2) {
+            const double a = v[(mb + q) * ldp], b = v[(mb + q + 1) * ldp];
+            m0 = fma(a, us[q], m0); s0 = fma(a, a, s0);
+            m1 = fma(b, us[q + 1], m1); s1 = fma(b, b, s1);
+        }
+        if (q < lim) { const double a = v[(mb + q) * ldp]; m0 = fma(a, us[q], m0); s0 = fma(a, a, s0); }
+    }
+    if (live) {
+        mu[r * ncol + col] = m0 + m1;
+        var[r * ncol + col] = amp - (s0 + s1);
+    }
+}
+
+__global__ void dot_self_kernel(const double* __restrict__ ysol, long M, double* __restrict__ out) {
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (long m = threadIdx.x; m < M; m += blockDim.x) { const double u = ysol[m * 16]; acc = fma(u, u, acc); }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+
+static gemm::Task mk(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int M, int N, int K, int lower) {
+    gemm::Task t;
+    memset(&t, 0, sizeof t);
+    t.A = A; t.lda = lda; t.B = B; t.ldb = ldb; t.C = C; t.ldc = ldc; t.M = M; t.N = N; t.K = K;
+    t.alpha = 1.0; t.beta = 0.0; t.lower = lower;
+    return t;
+}
+
+// Runs the device pipeline up to `stage`: 0 = through Cholesky + u (logl only), 1 = everything.
+static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
+    gb_ctx* ctx = p->ctx;
+    cudaStream_t s = ctx->stream;
+    if (!p->have_data) return gb_fail(ctx, GB_ERR_ARG, "gb_predict before gb_problem_set_data");
+    CovParams cp;
+    GB_TRY(fill_cov_params(ctx, cp, h->kernel_id, h->gp_length, h->coeffm, h->gp_amp));
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const long Ns = p->Ns, M = p->M, Mp = p->Mp, ldp = p->ldp, ncp = p->ncp, ncol = p->ncol;
+
+    GB_CUDA(ctx, cudaEventRecord(p->ev[0], s));
+    // ---- reset pads / accumulators
+    GB_CUDA(ctx, cudaMemsetAsync(p->Bm, 0, (size_t)Mp * Mp * sizeof(double), s));
+    GB_CUDA(ctx, cudaMemsetAsync(p->scal, 0, 4 * sizeof(double), s));
+    GB_CUDA(ctx, cudaMemsetAsync(p->info, 0, 4 * sizeof(int), s));
+    if (Mp > M) GB_CUDA(ctx, cudaMemsetAsync(p->Pt + M * ldp, 0, (size_t)(Mp - M) * ldp * sizeof(double), s));
+    if (ncp > ncol)
+        for (int r = 0; r < 3; ++r)
+            GB_CUDA(ctx, cudaMemset2DAsync(p->Pt + r * ncp + ncol, ldp * sizeof(double), 0, (ncp - ncol) * sizeof(double), Mp, s));
+    GB_CUDA(ctx, cudaMemcpyAsync(p->ydev, p->y_host_pinned, M * sizeof(double), cudaMemcpyHostToDevice, s));
+    set_y_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(p->ydev, M, Mp, p->ysol);
+    GB_CUDA(ctx, cudaGetLastError());
+    // ---- stationary covariance tables (kernels.create_cov evaluated once per lattice offset)
+    GB_CUDA(ctx, launch_cov_tables(cp, p->n, p->vox, p->tables, s));
+    GB_CUDA(ctx, cudaEventRecord(p->ev[1], s));
+
+    // ---- Pt = A3 . K : fused assembly + projection, 6 (data block c, property block r) products
+    {
+        gemm::TaskBatch b;
+        b.n = 0;
+        for (int c = 0; c < 2; ++c)
+            for (int r = 0; r < 3; ++r) {
+                gemm::Task t = mk(p->A[c], p->lda, p->tables + (long)(c * 3 + r) * p->ext + p->C0, 0,
+                                  p->Pt + (long)c * Ns * ldp + r * ncp, ldp, (int)Ns, (int)ncol, (int)p->Kp, 0);
+                t.Lrow = p->L + p->c0;
+                t.Lcol = p->L;
+                b.t[b.n++] = t;
+            }
+        GB_CUDA(ctx, gemm::launch(b, gemm::B_GEN, s));
+    }
+    GB_CUDA(ctx, cudaEventRecord(p->ev[2], s));
+    if (p->nd) {
+        dim3 grid((unsigned)((ncol + 255) / 256), (unsigned)p->nd, 3);
+        drill_rows_pt_kernel<<<grid, 256, 0, s>>>(p->tables, p->ext, p->C0, p->L, p->drill_dev, p->c0, ncol, ncp, ldp, 2 * Ns, p->Pt);
+        GB_CUDA(ctx, cudaGetLastError());
+    }
+    GB_CUDA(ctx, cudaEventRecord(p->ev[3], s));
+
+    // ---- AkA = A3 . Pt^T (lower triangle) over this rank's voxel columns
+    {
+        gemm::TaskBatch b;
+        b.n = 3;
+        b.t[0] = mk(p->A[0] + p->c0, p->lda, p->Pt, ldp, p->Bm, Mp, (int)Ns, (int)Ns, (int)ncp, 1);
+        b.t[1] = mk(p->A[1] + p->c0, p->lda, p->Pt + ncp, ldp, p->Bm + Ns * Mp, Mp, (int)Ns, (int)Ns, (int)ncp, 0);
+        b.t[2] = mk(p->A[1] + p->c0, p->lda, p->Pt + Ns * ldp + ncp, ldp, p->Bm + Ns * Mp + Ns, Mp, (int)Ns, (int)Ns, (int)ncp, 1);
+        GB_CUDA(ctx, gemm::launch(b, gemm::B_T, s));
+        if (p->nd) {
+            dim3 grid((unsigned)((M + 255) / 256), (unsigned)p->nd);
+            drill_rows_aka_kernel<<<grid, 256, 0, s>>>(p->Pt, ldp, ncp, p->drill_dev, p->c0, p->c1, 2 * Ns, M, p->Bm, Mp);
+            GB_CUDA(ctx, cudaGetLastError());
+        }
+    }
+    GB_CUDA(ctx, cudaEventRecord(p->ev[4], s));
+    GB_TRY(comm_allreduce_sum_f64(ctx, p->Bm, (size_t)Mp * Mp));
+    add_noise_diag_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(p->Bm, Mp, Ns, M, Mp, h->gp_sigma[0], h->gp_sigma[1], h->gp_sigma[2]);
+    GB_CUDA(ctx, cudaGetLastError());
+    GB_CUDA(ctx, cudaEventRecord(p->ev[5], s));
+
+    // ---- Cholesky (inversion.py:100) and u = L^-1 y (:105)
+    CholWork w;
+    w.linv = p->linv; w.logdet = p->scal; w.info = p->info;
+    GB_CUDA(ctx, chol_factor(p->Bm, Mp, (int)Mp, (int)M, w, s));
+    GB_CUDA(ctx, cudaEventRecord(p->ev[6], s));
+    GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->ysol, 16, 1, p->ytmp, s));
+    dot_self_kernel<<<1, 256, 0, s>>>(p->ysol, M, p->scal + 1);
+    GB_CUDA(ctx, cudaGetLastError());
+    if (full) {
+        // ---- V = L^-1 Pt (:114) in place, then mean (:115) and variance diagonal (:117)
+        GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->Pt, ldp, (int)ldp, p->tmp, s));
+        GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
+        dim3 grid((unsigned)((ncp + 255) / 256), 3);
+        mean_var_kernel<<<grid, 256, 0, s>>>(p->Pt, ldp, ncp, ncol, M, p->ysol, h->gp_amp, p->mu, p->var);
+        GB_CUDA(ctx, cudaGetLastError());
+    } else {
+        GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
+    }
+    GB_CUDA(ctx, cudaEventRecord(p->ev[8], s));
+    return GB_OK;
+}
+
+static int collect_timings(gb_problem* p) {
+    gb_ctx* ctx = p->ctx;
+    const int map[8] = {GB_T_TABLES, GB_T_PROJECT, GB_T_DRILLROWS, GB_T_AKA, GB_T_ALLREDUCE, GB_T_CHOL, GB_T_TRSM, GB_T_MEANVAR};
+    for (int i = 0; i < 8; ++i) {
+        float t = 0.f;
+        GB_CUDA(ctx, cudaEventElapsedTime(&t, p->ev[i], p->ev[i + 1]));
+        p->ms[map[i]] = t;
+    }
+    float t = 0.f;
+    GB_CUDA(ctx, cudaEventElapsedTime(&t, p->ev[0], p->ev[8]));
+    p->ms[GB_T_TOTAL] = t;
+    return GB_OK;
+}
+
+extern "C" int gb_predict(gb_problem* p, const gb_hyper* h, int flags, double* mu, double* var, double* logl, int* info) {
+    if (!p || !h) return GB_ERR_ARG;
+    gb_ctx* ctx = p->ctx;
+    const bool full = (flags & (GB_FLAG_MEAN | GB_FLAG_VAR)) != 0;
+    GB_TRY(run_predict(p, h, full));
+    cudaStream_t s = ctx->stream;
+    const long ncol = p->ncol;
+    double* o = p->out_pinned;
+    GB_CUDA(ctx, cudaEventRecord(p->ev[9], s));
+    if (full && mu) GB_CUDA(ctx, cudaMemcpyAsync(o, p->mu, 3 * ncol * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (full && var) GB_CUDA(ctx, cudaMemcpyAsync(o + 3 * ncol, p->var, 3 * ncol * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GB_CUDA(ctx, cudaMemcpyAsync(o + 6 * ncol, p->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GB_CUDA(ctx, cudaMemcpyAsync(o + 6 * ncol + 2, p->info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GB_CUDA(ctx, cudaEventRecord(p->ev[10], s));
+    GB_CUDA(ctx, cudaStreamSynchronize(s));
+    GB_TRY(collect_timings(p));
+    {
+        float t = 0.f;
+        GB_CUDA(ctx, cudaEventElapsedTime(&t, p->ev[9], p->ev[10]));
+        p->ms[GB_T_D2H] = t;
+    }
+    int inf = 0;
+    memcpy(&inf, o + 6 * ncol + 2, sizeof(int));
+    if (info) *info = inf;
+    if (full && mu) memcpy(mu, o, 3 * ncol * sizeof(double));
+    if (full && var) memcpy(var, o + 3 * ncol, 3 * ncol * sizeof(double));
+    if (logl) {
+        // inversion.py:107-110 (Q5: N_vox log 2 pi, not M)
+        const double logdet = o[6 * ncol], uu = o[6 * ncol + 1];
+        *logl = -0.5 * (uu + logdet + (double)p->N * log(2.0 * M_PI));
+    }
+    return inf > 0 ? inf : GB_OK;
+}
+
+extern "C" int gb_neg_logl(gb_problem* p, const gb_hyper* h, double* neg_logl, int* info) {
+    if (!p || !h || !neg_logl) return GB_ERR_ARG;
+    gb_ctx* ctx = p->ctx;
+    GB_TRY(run_predict(p, h, false));
+    double sc[2];
+    int inf = 0;
+    GB_CUDA(ctx, cudaMemcpyAsync(p->out_pinned, p->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(p->out_pinned + 2, p->info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GB_TRY(collect_timings(p));
+    memcpy(sc, p->out_pinned, sizeof sc);
+    memcpy(&inf, p->out_pinned + 2, sizeof(int));
+    if (info) *info = inf;
+    const double logl = -0.5 * (sc[1] + sc[0]);   // inversion.py:148 (no N log 2 pi)
+    *neg_logl = (inf > 0 || !isfinite(logl)) ? INFINITY : -logl;   // :150-152
+    return GB_OK;
+}
+
+extern "C" int gb_problem_get_sens(gb_problem* p, int kind, double* out) {
+    if (!p || !out || (kind != GB_SENS_GRAV && kind != GB_SENS_MAGN)) return GB_ERR_ARG;
+    gb_ctx* ctx = p->ctx;
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GB_CUDA(ctx, cudaMemcpy2DAsync(out, p->N * sizeof(double), p->A[kind], p->lda * sizeof(double), p->N * sizeof(double), p->Ns,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+extern "C" int gb_forward(gb_problem* p, int kind, const double* x, double* out) {
+    if (!p || !x || !out || (kind != GB_SENS_GRAV && kind != GB_SENS_MAGN)) return GB_ERR_ARG;
+    gb_ctx* ctx = p->ctx;
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<double> xd, yd;
+    GB_CUDA(ctx, xd.alloc(p->N));
+    GB_CUDA(ctx, yd.alloc(p->Ns));
+    GB_CUDA(ctx, cudaMemcpyAsync(xd.p, x, p->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, launch_gemv(p->A[kind], p->Ns, p->N, p->lda, xd.p, yd.p, ctx->stream));
+    GB_CUDA(ctx, cudaMemcpyAsync(out, yd.p, p->Ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+// Dense posterior covariance  K - V^T V  (inversion.py:117) for callers that read Inversion.cov_rec; small cubes only.
+__global__ void posterior_cov_kernel(const double* __restrict__ tables, long ext, long C0, const int* __restrict__ L,
+                                     const double* __restrict__ V, long ldp, long ncp, long N, long M, double* __restrict__ out) {
+    __shared__ double va[16][17], vb[16][17];
+    const long a = (long)blockIdx.y * 16 + threadIdx.y, b = (long)blockIdx.x * 16 + threadIdx.x;   // rows / cols of the 3N x 3N output
+    const long a_load = (long)blockIdx.y * 16 + threadIdx.x, b_load = b;
+    const long n3 = 3 * N;
+    double acc = 0.0;
+    for (long m0 = 0; m0 < M; m0 += 16) {
+        const long m = m0 + threadIdx.y;
+        va[threadIdx.y][threadIdx.x] = (m < M && a_load < n3) ? V[m * ldp + (a_load / N) * ncp + a_load % N] : 0.0;
+        vb[threadIdx.y][threadIdx.x] = (m < M && b_load < n3) ? V[m * ldp + (b_load / N) * ncp + b_load % N] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc = fma(va[q][threadIdx.y], vb[q][threadIdx.x], acc);
+        __syncthreads();
+    }
+    if (a < n3 && b < n3) {
+        const int ra = (int)(a / N), rb = (int)(b / N);
+        const double k = tables[(long)(ra * 3 + rb) * ext + C0 + (L[b % N] - L[a % N])];
+        out[a * n3 + b] = k - acc;
+    }
+}
+
+extern "C" int gb_posterior_cov(gb_problem* p, const gb_hyper* h, double* out) {
+    if (!p || !h || !out) return GB_ERR_ARG;
+    gb_ctx* ctx = p->ctx;
+    if (p->ncol != p->N) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "gb_posterior_cov needs an unsharded problem");
+    if (3 * p->N > 46000) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "dense 3N x 3N posterior covariance refused for N=%lld", (long long)p->N);
+    GB_TRY(run_predict(p, h, true));
+    const long n3 = 3 * p->N;
+    DevBuf<double> o;
+    GB_CUDA(ctx, o.alloc((size_t)n3 * n3));
+    dim3 grid((unsigned)((n3 + 15) / 16), (unsigned)((n3 + 15) / 16)), block(16, 16);
+    posterior_cov_kernel<<<grid, block, 0, ctx->stream>>>(p->tables, p->ext, p->C0, p->L, p->Pt, p->ldp, p->ncp, p->N, p->M, o.p);
+    GB_CUDA(ctx, cudaGetLastError());
+    GB_CUDA(ctx, cudaMemcpyAsync(out, o.p, (size_t)n3 * n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int inf = 0;
+    GB_CUDA(ctx, cudaMemcpy(&inf, p->info, sizeof(int), cudaMemcpyDeviceToHost));
+    return inf > 0 ? inf : GB_OK;
+}
+
+extern "C" int gb_get_timings(gb_problem* p, double* ms, int n) {
+    if (!p || !ms) return GB_ERR_ARG;
+    for (int i = 0; i < n && i < GB_NUM_TIMERS; ++i) ms[i] = p->ms[i];
+    return GB_OK;
+}

@@ -1,0 +1,82 @@
+// NCCL plumbing for the multi-GPU path (one process per GPU).  libnccl is resolved lazily with
+// dlopen so that the single-GPU library has no load-time dependency on it; the only collective on
+// the data path is the all-reduce of the per-shard AkA partial sums.
+#include <dlfcn.h>
+
+#include "common.cuh"
+#include "comm.h"
+
+namespace {
+typedef struct { char internal[128]; } ncclUniqueId_;
+typedef int (*fn_getuid)(ncclUniqueId_*);
+typedef int (*fn_initrank)(void**, int, ncclUniqueId_, int);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_destroy)(void*);
+typedef const char* (*fn_errstr)(int);
+
+struct NcclApi {
+    void* handle = nullptr;
+    fn_getuid get_uid = nullptr;
+    fn_initrank init_rank = nullptr;
+    fn_allreduce all_reduce = nullptr;
+    fn_destroy destroy = nullptr;
+    fn_errstr errstr = nullptr;
+} g_nccl;
+
+int load_nccl(gb_ctx* ctx) {
+    if (g_nccl.handle) return GB_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) return gb_fail(ctx, GB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.get_uid = (fn_getuid)dlsym(g_nccl.handle, "ncclGetUniqueId");
+    g_nccl.init_rank = (fn_initrank)dlsym(g_nccl.handle, "ncclCommInitRank");
+    g_nccl.all_reduce = (fn_allreduce)dlsym(g_nccl.handle, "ncclAllReduce");
+    g_nccl.destroy = (fn_destroy)dlsym(g_nccl.handle, "ncclCommDestroy");
+    g_nccl.errstr = (fn_errstr)dlsym(g_nccl.handle, "ncclGetErrorString");
+    if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.all_reduce || !g_nccl.destroy)
+        return gb_fail(ctx, GB_ERR_NCCL, "libnccl is missing required symbols");
+    return GB_OK;
+}
+}  // namespace
+
+extern "C" int gb_comm_unique_id(gb_ctx* ctx, void* id128) {
+    if (!ctx || !id128) return gb_fail(ctx, GB_ERR_ARG, "gb_comm_unique_id: null argument");
+    GB_TRY(load_nccl(ctx));
+    ncclUniqueId_ id;
+    int rc = g_nccl.get_uid(&id);
+    if (rc != 0) return gb_fail(ctx, GB_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    memcpy(id128, &id, 128);
+    return GB_OK;
+}
+
+extern "C" int gb_comm_init(gb_ctx* ctx, const void* id128, int rank, int nranks) {
+    if (!ctx || !id128 || rank < 0 || nranks < 1 || rank >= nranks) return gb_fail(ctx, GB_ERR_ARG, "gb_comm_init: bad argument");
+    GB_TRY(load_nccl(ctx));
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId_ id;
+    memcpy(&id, id128, 128);
+    void* comm = nullptr;
+    int rc = g_nccl.init_rank(&comm, nranks, id, rank);
+    if (rc != 0) return gb_fail(ctx, GB_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return GB_OK;
+}
+
+int comm_allreduce_sum_f64(gb_ctx* ctx, double* buf, size_t count) {
+    if (ctx->nranks <= 1) return GB_OK;
+    if (!ctx->nccl_comm) return gb_fail(ctx, GB_ERR_NCCL, "multi-rank problem without gb_comm_init");
+    const int ncclFloat64 = 8, ncclSum = 0;
+    int rc = g_nccl.all_reduce(buf, buf, count, ncclFloat64, ncclSum, ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return gb_fail(ctx, GB_ERR_NCCL, "ncclAllReduce: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    return GB_OK;
+}
+
+void comm_destroy(gb_ctx* ctx) {
+    if (ctx->nccl_comm && g_nccl.destroy) g_nccl.destroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+}

@@ -1,0 +1,129 @@
+// Shared declarations of libgeobo_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/geobo_b200.h"
+
+struct gb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // NCCL (resolved lazily with dlopen, see comm.cu)
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+extern std::string g_gb_create_error;
+
+inline int gb_fail(gb_ctx* ctx, int code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
+inline int gb_fail(gb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_gb_create_error = buf;
+    return code;
+}
+
+#define GB_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return gb_fail(ctx, e__ == cudaErrorMemoryAllocation ? GB_ERR_NOMEM : GB_ERR_CUDA,      \
+                           "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));     \
+    } while (0)
+
+#define GB_TRY(call)                  \
+    do {                              \
+        int rc__ = (call);            \
+        if (rc__ != GB_OK) return rc__; \
+    } while (0)
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// RAII device buffer used for scratch inside one API call
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        n = count;
+        return cudaMalloc((void**)&p, count * sizeof(T) + 16);
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+// ---------------------------------------------------------------------------- covariance functions (cov.cu)
+struct CovParams {
+    int kernel_id;
+    double l[3];   // de-duplicated length scales
+    double w[3];   // w1 (0-2), w2 (1-2), w3 (0-1)
+    double amp;
+};
+
+// ---------------------------------------------------------------------------- fp64 tensor-pipe GEMM engine (gemm_f64.cu)
+namespace gemm {
+enum BMode { B_T = 0, B_N = 1, B_GEN = 2 };
+struct Task {
+    const double* A;      // [M][lda], K contiguous
+    const double* B;      // B_T: [N][ldb] (K contiguous); B_N: [K][ldb] (N contiguous); B_GEN: table base (+C0)
+    const double* Cin;    // used when beta != 0 (may alias C)
+    double* C;            // [M][ldc]
+    long lda, ldb, ldcin, ldc;
+    int M, N, K;          // K must be a multiple of 16 (operands zero padded)
+    int lower;            // skip tiles strictly above the diagonal
+    double alpha, beta;   // C = alpha * A.B + beta * Cin
+    const int* Lrow;      // B_GEN: extended-lattice id of output column n  (Lrow[n])
+    const int* Lcol;      // B_GEN: extended-lattice id of contraction index k (Lcol[k])
+};
+constexpr int MAX_TASKS = 6;
+struct TaskBatch {
+    Task t[MAX_TASKS];
+    int n;
+};
+// Launches one grid covering all tasks in the batch (blockIdx.z = task).
+cudaError_t launch(const TaskBatch& batch, BMode mode, cudaStream_t stream);
+cudaError_t init();
+}  // namespace gemm
+
+// ---------------------------------------------------------------------------- kernel launchers
+cudaError_t launch_cov_tables(const CovParams& cp, const int64_t ncube[3], const double vox[3], double* tables /*9 x ext*/,
+                              cudaStream_t s);
+cudaError_t launch_lattice_ids(const int64_t ncube[3], int* L, int64_t n_padded, cudaStream_t s);
+cudaError_t launch_create_cov_dense(const CovParams& cp, const double* D2, int64_t n, double* out, cudaStream_t s);
+cudaError_t launch_create_cov_grid(const CovParams& cp, const int64_t ncube[3], const double vox[3], double* out,
+                                   cudaStream_t s);
+cudaError_t launch_grid_points(const int64_t lpix[3], const double sc[3], double* out, cudaStream_t s);
+cudaError_t launch_sqdist(const double* pts, int64_t n, int dim, double* out, cudaStream_t s);
+cudaError_t launch_a_sens(int kind, const double B[3], const double* loc, int64_t nsens, const double* edges,
+                          const int64_t ncube[3], double mul, double div, double* out, int64_t ld, int sm_count,
+                          cudaStream_t s);
+cudaError_t launch_cov_function(int kernel_id, int cross, const double* D2, int64_t count, double l1, double l2, double* out,
+                                cudaStream_t s);
+cudaError_t launch_corner_func(int kind, const double* x, const double* y, const double* z, int64_t count, const double B[3],
+                               double* out, cudaStream_t s);
+cudaError_t launch_a_drill(const double* loc, int64_t nd, const double* vp, int64_t N, double* out, cudaStream_t s);
+cudaError_t launch_gemv(const double* A, int64_t rows, int64_t cols, int64_t ld, const double* x, double* y,
+                        cudaStream_t s);
+
+// Cholesky / triangular solve (chol.cu)
+struct CholWork {
+    double* linv = nullptr;   // [Mp/128][128][128] inverses of the diagonal blocks
+    double* logdet = nullptr; // device scalar: sum log(L_ii^2)
+    int* info = nullptr;      // device scalar: first non-positive pivot (1-based), 0 = ok
+};
+cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, cudaStream_t s);
+// V = L^-1 Pt in place (Pt: [Mp][ldp]); tmp: [128][ldp]
+cudaError_t chol_forward_solve(const double* L, long ldl, int Mp, const CholWork& w, double* Pt, long ldp, int ncols,
+                               double* tmp, cudaStream_t s);

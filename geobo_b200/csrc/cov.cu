@@ -1,0 +1,273 @@
+// GP covariance functions (geobo/kernels.py) on the device, fp64, formula-for-formula.
+//
+//  * cov_value():            the nine blocks of kernels.create_cov (kernels.py:158-195)
+//  * cov_tables_kernel:      stationary tables over the EXTENDED difference lattice
+//                            (2yN-1)(2xN-1)(2zN-1): K[(c,j),(r,i)] = tab[c][r][L(i) - L(j) + C0],
+//                            L(v) = (vy (2xN-1) + vx)(2zN-1) + vz -- one integer subtraction per
+//                            covariance element inside the fused projection GEMM.
+//  * create_cov_dense_kernel: kernels.create_cov for an arbitrary user D2 (API compatibility).
+//  * create_cov_grid_kernel:  the same 3N x 3N matrix straight from the grid spec, staged in shared
+//                            memory and written with bulk async copies (UBLKCP) -- HBM-write bound.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------ formulas
+// The operation order follows the NumPy expressions so that results differ from the reference only
+// by the last-ulp differences of exp/sin/cos implementations.
+__device__ __forceinline__ double k_exp_same(double D2, double g) {        // kernels.py:88
+    return exp(__ddiv_rn(__dmul_rn(-0.5, D2), __dmul_rn(g, g)));
+}
+__device__ __forceinline__ double k_exp_cross(double D2, double l1, double l2) {   // kernels.py:99
+    const double s = __dadd_rn(__dmul_rn(l1, l1), __dmul_rn(l2, l2));
+    return __dmul_rn(sqrt(__ddiv_rn(__dmul_rn(__dmul_rn(2.0, l1), l2), s)), exp(-__ddiv_rn(D2, s)));
+}
+__device__ __forceinline__ double k_matern_same(double D2, double g) {     // kernels.py:145-146
+    const double nu = __ddiv_rn(__dmul_rn(sqrt(3.0), sqrt(D2)), g);
+    return __dmul_rn(__dadd_rn(1.0, nu), exp(-nu));
+}
+__device__ __forceinline__ double k_matern_cross(double D2, double l1, double l2) {   // kernels.py:153-156
+    const double norm = __ddiv_rn(__dmul_rn(2.0, sqrt(__dmul_rn(l1, l2))), __dsub_rn(__dmul_rn(l1, l1), __dmul_rn(l2, l2)));
+    const double sd = sqrt(__dmul_rn(3.0, D2));
+    const double a = __dmul_rn(l1, exp(__ddiv_rn(-sd, l1)));
+    const double b = __dmul_rn(l2, exp(__ddiv_rn(-sd, l2)));
+    return __dmul_rn(norm, __dsub_rn(a, b));
+}
+#define GB_PI 3.141592653589793
+__device__ __forceinline__ double k_sparse_same(double D2, double g) {     // kernels.py:108-114
+    const double d = sqrt(D2);
+    if (!(d < g)) return 0.0;
+    const double arg = __ddiv_rn(__dmul_rn(2.0 * GB_PI, d), g);
+    const double t1 = __dmul_rn(__ddiv_rn(__dadd_rn(2.0, cos(arg)), 3.0), __dsub_rn(1.0, __ddiv_rn(d, g)));
+    const double t2 = __dmul_rn(1.0 / (2.0 * GB_PI), sin(arg));
+    const double r = __dadd_rn(t1, t2);
+    return r < 0.0 ? 0.0 : r;
+}
+__device__ __forceinline__ double k_sparse_cross(double D2, double l1, double l2) {   // kernels.py:121-138
+    const double d = sqrt(D2);
+    if (l1 == l2) l2 = __dadd_rn(l2, __dmul_rn(1e-3, l2));                 // :125-126
+    const double lmean = __ddiv_rn(__dadd_rn(l1, l2), 2.0);
+    const double lmin = fmin(l1, l2), lmax = fmax(l1, l2);
+    const double half_diff = __ddiv_rn(fabs(__dsub_rn(l2, l1)), 2.0);
+    const double half_sum = __ddiv_rn(__dadd_rn(l1, l2), 2.0);
+    const double c0 = __ddiv_rn(2.0, __dmul_rn(3.0, sqrt(__dmul_rn(l1, l2))));
+    double res = 0.0;
+    if (d >= half_diff && d <= half_sum) {                                  // branch B wins ties (:135)
+        const double den = __dmul_rn(2.0 * GB_PI, __dsub_rn(__dmul_rn(l1, l1), __dmul_rn(l2, l2)));
+        const double l1c = __dmul_rn(__dmul_rn(l1, l1), l1), l2c = __dmul_rn(__dmul_rn(l2, l2), l2);
+        const double s1 = sin(__ddiv_rn(__dmul_rn(GB_PI, __dsub_rn(l2, __dmul_rn(2.0, d))), l1));
+        const double s2 = sin(__ddiv_rn(__dmul_rn(GB_PI, __dsub_rn(l1, __dmul_rn(2.0, d))), l2));
+        double v = __dsub_rn(lmean, d);
+        v = __dadd_rn(v, __ddiv_rn(__dmul_rn(l1c, s1), den));
+        v = __dsub_rn(v, __ddiv_rn(__dmul_rn(l2c, s2), den));
+        res = __dmul_rn(c0, v);
+    } else if (d <= half_diff) {                                            // branch A (:133), cosine inside the sine
+        const double lmax3 = __dmul_rn(__dmul_rn(lmax, lmax), lmax);
+        const double f = __ddiv_rn(__dmul_rn(1.0 / GB_PI, lmax3), __dsub_rn(__dmul_rn(lmax, lmax), __dmul_rn(lmin, lmin)));
+        const double inner = cos(__ddiv_rn(__dmul_rn(2.0 * GB_PI, d), lmax));
+        const double s = sin(__dmul_rn(__ddiv_rn(__dmul_rn(GB_PI, lmin), lmax), inner));
+        res = __dmul_rn(c0, __dadd_rn(lmin, __dmul_rn(f, s)));
+    }
+    return res < 0.0 ? 0.0 : res;
+}
+
+// Block (row-block r, column-block c) of create_cov: same-property kernel on the diagonal, otherwise
+// w(r,c) * cross(l_c, l_r)  (kernels.py:183-194: column strip c, vstack slot r, gammas = params[[c, r]]).
+// The amplitude multiplies the finished block (inversion.py:92: gp_amp * create_cov(...)).
+__device__ __forceinline__ double cov_value(const CovParams& P, int r, int c, double D2) {
+    double v;
+    if (r == c) {
+        const double g = P.l[c];
+        v = P.kernel_id == GB_KERNEL_EXP ? k_exp_same(D2, g)
+            : P.kernel_id == GB_KERNEL_MATERN32 ? k_matern_same(D2, g) : k_sparse_same(D2, g);
+    } else {
+        const double l1 = P.l[c], l2 = P.l[r];
+        const int lo = min(r, c), hi = max(r, c);
+        const double w = (lo == 0 && hi == 1) ? P.w[2] : (lo == 0 && hi == 2) ? P.w[0] : P.w[1];
+        v = P.kernel_id == GB_KERNEL_EXP ? k_exp_cross(D2, l1, l2)
+            : P.kernel_id == GB_KERNEL_MATERN32 ? k_matern_cross(D2, l1, l2) : k_sparse_cross(D2, l1, l2);
+        v = __dmul_rn(w, v);
+    }
+    return __dmul_rn(P.amp, v);
+}
+
+// squared distance of an integer lattice offset, summed x, y, z like kernels.py:46,54-58
+__device__ __forceinline__ double lattice_d2(int dx, int dy, int dz, double sx, double sy, double sz) {
+    const double ax = __dmul_rn((double)dx, sx), ay = __dmul_rn((double)dy, sy), az = __dmul_rn((double)dz, sz);
+    return __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+}
+
+// ------------------------------------------------------------------------------------ tables
+__global__ void cov_tables_kernel(CovParams P, int xN, int yN, int zN, double sx, double sy, double sz, double* tables) {
+    const int EX = 2 * xN - 1, EY = 2 * yN - 1, EZ = 2 * zN - 1;
+    const long ext = (long)EX * EY * EZ;
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ext) return;
+    const int ez = (int)(e % EZ);
+    const long t = e / EZ;
+    const int ex = (int)(t % EX), ey = (int)(t / EX);
+    const double D2 = lattice_d2(ex - (xN - 1), ey - (yN - 1), ez - (zN - 1), sx, sy, sz);
+    const int cr = blockIdx.y;   // c * 3 + r : row-block c (data side), column-block r (voxel side)
+    tables[(long)cr * ext + e] = cov_value(P, cr / 3, cr % 3, D2);
+}
+
+cudaError_t launch_cov_tables(const CovParams& cp, const int64_t n[3], const double vox[3], double* tables, cudaStream_t s) {
+    const long ext = (2 * n[0] - 1) * (2 * n[1] - 1) * (2 * n[2] - 1);
+    dim3 grid((unsigned)((ext + 255) / 256), 9);
+    cov_tables_kernel<<<grid, 256, 0, s>>>(cp, (int)n[0], (int)n[1], (int)n[2], vox[0], vox[1], vox[2], tables);
+    return cudaGetLastError();
+}
+
+// L(v) for every voxel (flat order (iy*xN+ix)*zN+iz); entries >= N repeat voxel 0 (zero-padded operand columns)
+__global__ void lattice_ids_kernel(int xN, int yN, int zN, int* L, long n_padded) {
+    const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_padded) return;
+    const long N = (long)xN * yN * zN;
+    const long vv = v < N ? v : 0;
+    const int iz = (int)(vv % zN);
+    const long t = vv / zN;
+    const int ix = (int)(t % xN), iy = (int)(t / xN);
+    L[v] = (iy * (2 * xN - 1) + ix) * (2 * zN - 1) + iz;
+}
+
+cudaError_t launch_lattice_ids(const int64_t n[3], int* L, int64_t n_padded, cudaStream_t s) {
+    lattice_ids_kernel<<<(unsigned)((n_padded + 255) / 256), 256, 0, s>>>((int)n[0], (int)n[1], (int)n[2], L, n_padded);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ dense create_cov(D2, ...)
+// out[(r*n + i) * 3n + c*n + j] = block(r, c)(D2[i, j]); one thread per D2 element, 9 coalesced stores.
+__global__ void create_cov_dense_kernel(CovParams P, const double* __restrict__ D2, long n, double* __restrict__ out) {
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long i = blockIdx.y;
+    if (j >= n) return;
+    const double d2 = D2[i * n + j];
+    const long ld = 3 * n;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[(r * n + i) * ld + c * n + j] = cov_value(P, r, c, d2);
+}
+
+cudaError_t launch_create_cov_dense(const CovParams& cp, const double* D2, int64_t n, double* out, cudaStream_t s) {
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    create_cov_dense_kernel<<<grid, 256, 0, s>>>(cp, D2, n, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ dense assembly from the grid spec
+// One CTA per (row i of one row-block r): the row's voxel coordinates are decoded once, the 3N
+// entries are produced in shared memory in chunks and written with cp.async.bulk (TMA 1-D bulk
+// store, SASS UBLKCP) so the SM never stalls on the store path.
+constexpr int ASM_CHUNK = 2048;   // doubles per staged chunk (16 KB), double buffered
+
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256) create_cov_grid_kernel(CovParams P, int xN, int yN, int zN, double sx, double sy,
+                                                              double sz, double* __restrict__ out) {
+    __shared__ __align__(128) double stage[2][ASM_CHUNK];
+    const long N = (long)xN * yN * zN;
+    const long row = blockIdx.x;            // 0 .. 3N-1
+    const int r = (int)(row / N);
+    const long i = row % N;
+    const int iz = (int)(i % zN);
+    const long ti = i / zN;
+    const int ix = (int)(ti % xN), iy = (int)(ti / xN);
+    double* orow = out + row * 3 * N;
+    const long total = 3 * N;
+    int buf = 0;
+    for (long base = 0; base < total; base += ASM_CHUNK, buf ^= 1) {
+        const int len = (int)min((long)ASM_CHUNK, total - base);
+        // the bulk store that last read this buffer (two chunks ago) must have finished reading smem
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        for (int q = threadIdx.x; q < len; q += blockDim.x) {
+            const long col = base + q;
+            const int c = (int)(col / N);
+            const long j = col % N;
+            const int jz = (int)(j % zN);
+            const long tj = j / zN;
+            const int jx = (int)(tj % xN), jy = (int)(tj / xN);
+            stage[buf][q] = cov_value(P, r, c, lattice_d2(jx - ix, jy - iy, jz - iz, sx, sy, sz));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned bytes = (unsigned)len * 8u;
+            if ((bytes & 15u) == 0 && ((((uintptr_t)(orow + base)) & 15) == 0)) {
+                bulk_store(orow + base, stage[buf], bytes);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            } else {
+                for (int q = 0; q < len; ++q) orow[base + q] = stage[buf][q];
+            }
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+cudaError_t launch_create_cov_grid(const CovParams& cp, const int64_t n[3], const double vox[3], double* out, cudaStream_t s) {
+    const long N = n[0] * n[1] * n[2];
+    create_cov_grid_kernel<<<(unsigned)(3 * N), 256, 0, s>>>(cp, (int)n[0], (int)n[1], (int)n[2], vox[0], vox[1], vox[2], out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ calcGridPoints3D / calcDistanceMatrix
+__global__ void grid_points_kernel(int xN, int yN, int zN, double sx, double sy, double sz, double* out) {
+    const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long N = (long)xN * yN * zN;
+    if (v >= N) return;
+    const int iz = (int)(v % zN);
+    const long t = v / zN;
+    const int ix = (int)(t % xN), iy = (int)(t / xN);
+    out[3 * v + 0] = __dmul_rn((double)(ix + 1), sx);   // kernels.py:37-39: arange(1, n+1) * scale
+    out[3 * v + 1] = __dmul_rn((double)(iy + 1), sy);
+    out[3 * v + 2] = __dmul_rn((double)(iz + 1), sz);
+}
+
+cudaError_t launch_grid_points(const int64_t lpix[3], const double sc[3], double* out, cudaStream_t s) {
+    const long N = lpix[0] * lpix[1] * lpix[2];
+    grid_points_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>((int)lpix[0], (int)lpix[1], (int)lpix[2], sc[0], sc[1], sc[2], out);
+    return cudaGetLastError();
+}
+
+__global__ void sqdist_kernel(const double* __restrict__ pts, long n, int dim, double* __restrict__ out) {
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long i = blockIdx.y;
+    if (j >= n) return;
+    double acc = 0.0;
+    for (int d = 0; d < dim; ++d) {           // kernels.py:46,54-58: sum over dimensions in order
+        const double delta = __dsub_rn(pts[j * dim + d], pts[i * dim + d]);
+        acc = __dadd_rn(acc, __dmul_rn(delta, delta));
+    }
+    out[i * n + j] = acc;
+}
+
+cudaError_t launch_sqdist(const double* pts, int64_t n, int dim, double* out, cudaStream_t s) {
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    sqdist_kernel<<<grid, 256, 0, s>>>(pts, n, dim, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ elementwise API kernels
+// kernels.gpkernel / gpkernel2 / gpkernel_sparse / gpkernel_sparse2 / gpkernel_matern32 / gpkernel_matern32_2
+// (kernels.py:81-156) applied to an arbitrary array of squared distances.
+__global__ void cov_function_kernel(int kernel_id, int cross, const double* __restrict__ D2, long count, double l1, double l2,
+                                    double* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double d2 = D2[i];
+    double v;
+    if (!cross)
+        v = kernel_id == GB_KERNEL_EXP ? k_exp_same(d2, l1) : kernel_id == GB_KERNEL_MATERN32 ? k_matern_same(d2, l1) : k_sparse_same(d2, l1);
+    else
+        v = kernel_id == GB_KERNEL_EXP ? k_exp_cross(d2, l1, l2)
+            : kernel_id == GB_KERNEL_MATERN32 ? k_matern_cross(d2, l1, l2) : k_sparse_cross(d2, l1, l2);
+    out[i] = v;
+}
+
+cudaError_t launch_cov_function(int kernel_id, int cross, const double* D2, int64_t count, double l1, double l2, double* out,
+                                cudaStream_t s) {
+    cov_function_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(kernel_id, cross, D2, count, l1, l2, out);
+    return cudaGetLastError();
+}

@@ -1,0 +1,168 @@
+/*
+ * geobo_b200 -- C ABI of the B200-native GeoBO joint-inversion hot path.
+ *
+ * The reference (sebhaan/geobo) is pure Python with no FFI of its own; its boundary for
+ * this path is the Python module surface geobo.kernels / geobo.sensormodel /
+ * geobo.inversion.  Each entry point below names the reference interface it replaces
+ * (file:line in the reference tree).  INTEGRATION.md shows the ctypes stubs a maintainer
+ * of the reference would add to call them.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = error (text via gb_last_error),
+ *     >0 only from gb_predict/gb_neg_logl = LAPACK-style index (1-based) of the first
+ *     non-positive pivot of the Cholesky of A K A^T + Sigma;
+ *   - plain pointers and sizes only; all arrays are C-contiguous float64 / int64 unless
+ *     noted; the caller owns every host buffer, the library owns all device memory;
+ *   - one calling thread per gb_ctx; no callbacks, no exceptions across the boundary;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with GB_ERR_CUDA.
+ */
+#ifndef GEOBO_B200_H
+#define GEOBO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_OK 0
+#define GB_ERR_ARG (-1)
+#define GB_ERR_CUDA (-2)
+#define GB_ERR_NCCL (-3)
+#define GB_ERR_NOMEM (-4)
+#define GB_ERR_UNSUPPORTED (-5)
+
+/* kernel families, geobo/kernels.py:183-194 ('sparse' is the reference default) */
+#define GB_KERNEL_SPARSE 0
+#define GB_KERNEL_EXP 1
+#define GB_KERNEL_MATERN32 2
+
+/* forward-model kinds, geobo/sensormodel.py:71-74 */
+#define GB_SENS_GRAV 0
+#define GB_SENS_MAGN 1
+
+/* gb_predict flags */
+#define GB_FLAG_MEAN 1     /* posterior mean         (inversion.py:115) */
+#define GB_FLAG_VAR 2      /* diag of posterior cov. (inversion.py:117,238) */
+#define GB_FLAG_LOGL 4     /* log marginal likelihood (inversion.py:107-110) */
+#define GB_FLAG_ALL 7
+
+#define GB_NUM_TIMERS 16
+/* indices into gb_get_timings() (milliseconds, CUDA events on the context stream) */
+#define GB_T_SENS 0        /* A_sens x2 (problem_create)          */
+#define GB_T_TABLES 1      /* stationary covariance tables        */
+#define GB_T_PROJECT 2     /* Pt = A . K  (fused assembly + GEMM) */
+#define GB_T_DRILLROWS 3   /* drill rows of Pt / AkA gathers      */
+#define GB_T_AKA 4         /* AkA = A . Pt^T + Sigma              */
+#define GB_T_ALLREDUCE 5   /* NCCL all-reduce of AkA (multi-GPU)  */
+#define GB_T_CHOL 6        /* Cholesky of AkA                     */
+#define GB_T_TRSM 7        /* V = L^-1 Pt, u = L^-1 y             */
+#define GB_T_MEANVAR 8     /* mean, variance diag, logl           */
+#define GB_T_TOTAL 9       /* whole gb_predict on device          */
+#define GB_T_D2H 10        /* result copies to host               */
+
+typedef struct gb_ctx gb_ctx;
+typedef struct gb_problem gb_problem;
+
+/* ------------------------------------------------------------------ context */
+int gb_version(void);
+/* device < 0: use the current device. */
+int gb_ctx_create(int device, gb_ctx** out);
+int gb_ctx_destroy(gb_ctx* ctx);
+/* last error text of this context (ctx == NULL: of the last failed gb_ctx_create). */
+const char* gb_last_error(const gb_ctx* ctx);
+int gb_device_info(gb_ctx* ctx, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor,
+                   uint64_t* free_bytes, uint64_t* total_bytes);
+
+/* Multi-GPU (one process per GPU).  gb_comm_unique_id fills a 128-byte NCCL id on rank 0;
+ * the host distributes it (e.g. torch.distributed / a file) and every rank calls gb_comm_init. */
+int gb_comm_unique_id(gb_ctx* ctx, void* id128);
+int gb_comm_init(gb_ctx* ctx, const void* id128, int rank, int nranks);
+
+/* ------------------------------------------------------------------ geobo/kernels.py */
+/* kernels.calcGridPoints3D(Lpix, pixscale)  (kernels.py:27-42): out[(iy*xN+ix)*zN+iz][0..2] */
+int gb_grid_points(gb_ctx* ctx, const int64_t lpix[3], const double pixscale[3], double* out);
+/* kernels.calcDistanceMatrix(points)        (kernels.py:45-61): out[n*n] squared distances */
+int gb_sqdist(gb_ctx* ctx, const double* points, int64_t n, int dim, double* out);
+/* kernels.create_cov(D2, gplength, crossweights, fkernel) (kernels.py:158-195).
+ * gplength must already be de-duplicated (kernels.py:174-180 is host logic because it mutates
+ * the caller's ndarray); out is (3n)x(3n). */
+int gb_create_cov(gb_ctx* ctx, const double* D2, int64_t n, const double gplength[3], const double crossweights[3],
+                  int kernel_id, double* out);
+/* kernels.gpkernel / gpkernel_sparse / gpkernel_matern32 (cross = 0, kernels.py:81-88,101-114,140-146) and
+ * gpkernel2 / gpkernel_sparse2 / gpkernel_matern32_2 (cross = 1, gammas = (l1, l2), kernels.py:90-99,116-138,148-156)
+ * applied elementwise to `count` squared distances. */
+int gb_cov_function(gb_ctx* ctx, int kernel_id, int cross, const double* D2, int64_t count, double l1, double l2, double* out);
+/* Same matrix generated on the device from the grid spec alone (no D2 input): the HBM-write-bound
+ * assembly kernel.  out may be NULL (device only, for timing); ms receives the kernel time. */
+int gb_create_cov_grid(gb_ctx* ctx, const int64_t ncube[3], const double voxsize[3], const double gplength[3],
+                       const double crossweights[3], double amp, int kernel_id, double* out, float* ms);
+
+/* ------------------------------------------------------------------ geobo/sensormodel.py */
+/* sensormodel.A_sens(magneticField, locations, Edges, func) (sensormodel.py:29-93).
+ * edges: (3, yN+1, xN+1, zN+1); locations: (nsens, 3); out: (nsens, xN*yN*zN).
+ * out = (mul * s) / div with s the 8-corner difference: grav: mul = c_MILLIGALS_UNITS, div = fcor_grav;
+ * magn: mul = 1, div = fcor_mag (sensormodel.py:88-91). */
+int gb_a_sens(gb_ctx* ctx, int kind, const double B[3], const double* locations, int64_t nsens, const double* edges,
+              const int64_t ncube[3], double mul, double div, double* out);
+
+/* sensormodel.grav_func(x, y, z) / magn_func(x, y, z, bx, by, bz) (sensormodel.py:96-133), elementwise. */
+int gb_corner_func(gb_ctx* ctx, int kind, const double* x, const double* y, const double* z, int64_t count, const double B[3],
+                   double* out);
+/* sensormodel.A_drill(loc, voxelpos) (sensormodel.py:136-153): loc (3, ndrill), voxelpos (3, nvox) -> out (ndrill, nvox). */
+int gb_a_drill(gb_ctx* ctx, const double* loc, int64_t ndrill, const double* voxelpos, int64_t nvox, double* out);
+
+/* ------------------------------------------------------------------ geobo/inversion.py */
+typedef struct gb_problem_desc {
+    int64_t ncube[3];          /* xNcube, yNcube, zNcube                                   */
+    double voxsize[3];         /* xvoxsize, yvoxsize, zvoxsize (config_loader.py:56-58)    */
+    const double* edges;       /* (3, yN+1, xN+1, zN+1)  Inversion.Edges (inversion.py:61-66) */
+    const double* locations;   /* (nsens, 3) sensor_locations; nsens must equal xN*yN (sensormodel.py:54,58) */
+    int64_t nsens;
+    double magnetic_field[3];  /* magneticField (config_loader.py:46)                      */
+    double grav_mul, grav_div; /* c_MILLIGALS_UNITS, fcor_grav                             */
+    double magn_mul, magn_div; /* 1.0, fcor_mag                                            */
+    const int64_t* drill_idx;  /* flat voxel index of every drill row (A_drill one-hot column, sensormodel.py:136-153) */
+    int64_t ndrill;
+    /* voxel-column shard [col_begin, col_end) of Pt = A.K owned by this rank (0, N on one GPU) */
+    int64_t col_begin, col_end;
+} gb_problem_desc;
+
+typedef struct gb_hyper {
+    double gp_length[3];       /* effective (de-duplicated) length scales                  */
+    double gp_sigma[3];        /* noise std per data group (inversion.py:94)               */
+    double coeffm[3];          /* cross weights w1,w2,w3 (kernels.py:181)                  */
+    double gp_amp;             /* amplitude (inversion.py:92)                              */
+    int kernel_id;             /* GB_KERNEL_*                                              */
+    int reserved;
+} gb_hyper;
+
+/* Builds the device-resident problem: computes both sensitivity matrices on the GPU
+ * (Inversion.cubing, inversion.py:216-230, without materialising the zero-padded Asens3). */
+int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* desc, gb_problem** out);
+int gb_problem_destroy(gb_problem* p);
+/* Fs3 = normalised [grav, mag, drill] data vector, length M = 2*nsens + ndrill (inversion.py:221). */
+int gb_problem_set_data(gb_problem* p, const double* fs3);
+/* Inversion.predict3 (inversion.py:77-122) without the 3N x 3N covariance:
+ * mu and var = diag(cov) are returned for this rank's voxel-column shard as [3][col_end - col_begin]
+ * (property-major; the whole 3N vector on one GPU); logl and info are identical on every rank.
+ * mu / var / logl may be NULL (results stay on the device).  Returns info (>0) if AkA is not PD. */
+int gb_predict(gb_problem* p, const gb_hyper* h, int flags, double* mu, double* var, double* logl, int* info);
+/* Inversion.calc_logl (inversion.py:125-152): returns -logl without the N log(2 pi) term; +inf if not PD. */
+int gb_neg_logl(gb_problem* p, const gb_hyper* h, double* neg_logl, int* info);
+/* Asens_grav / Asens_mag as dense host arrays (nsens x N) -- for callers that read Inversion.Asens3. */
+int gb_problem_get_sens(gb_problem* p, int kind, double* out);
+/* simcube.create_synsurvey (simcube.py:147-150): out[nsens] = A_kind . x[N] */
+int gb_forward(gb_problem* p, int kind, const double* x, double* out);
+/* Dense posterior covariance block (small cubes only; inversion.py:117): out (3N x 3N). */
+int gb_posterior_cov(gb_problem* p, const gb_hyper* h, double* out);
+int gb_get_timings(gb_problem* p, double* ms, int n);
+/* bytes of device memory held by the problem */
+uint64_t gb_problem_device_bytes(gb_problem* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOBO_B200_H */
