@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the GeoBO joint-inversion hot path on B200 (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+
+Metric (BASELINE.json): voxels/sec of the joint inversion = N_voxels / time(covariance assembly +
+projection A.K.A^T + Cholesky + triangular solves + posterior mean + variance diagonal) -- the
+``Inversion.predict3`` stage.  A "step" is one such inversion of the named synthetic cube.
+
+  value     device-resident inputs (sensitivities, data vector in HBM), timed per step with CUDA events on the
+            library's stream and cross-checked by host wall clock between synchronisation points; max over ranks.
+  e2e       the same metric through the public Python API, ``Inversion.cubing(...)`` with HOST NumPy arrays:
+            includes building the device problem (sensitivity matrices on the GPU), every H2D copy and the D2H
+            of the six result cubes.
+  roofline  the dominant kernel (fused covariance assembly + projection on the fp64 DMMA tensor pipe).
+  cpu_baseline  the oracle's lean NumPy/SciPy restatement of the reference on this box's host cores (bounded sample).
+
+For N > 1 (torchrun) the voxel columns of Pt = A.K are sharded over ranks; the only data-path collective
+is the NCCL all-reduce of AkA inside the library (strong scaling: the cube is fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# BASELINE.json configs.  cfg2 is the default: "32x32x32 cube, grav+mag joint inversion,
+# sqexp kernel, fp64, 1xB200" (configs[1]).
+WORKLOADS = {
+    "cfg1": dict(shape=(25, 16, 16), kernel="sparse", nd=256, name="25x16x16 example-1 cube (sparse, nd=256)"),
+    "cfg1b": dict(shape=(16, 16, 16), kernel="exp", nd=50, name="16x16x16 cube (exp, nd=50)"),
+    "cfg2": dict(shape=(32, 32, 32), kernel="exp", nd=0, name="32x32x32 cube, grav+mag joint inversion, sqexp kernel, fp64"),
+    "cfg3": dict(shape=(64, 64, 32), kernel="matern32", nd=50, gl_mult=(1.0, 1.01, 1.02),
+                 name="64x64x32 cube, grav+mag + 50 drill constraints, Matern-3/2 cross-cov (fp64 path)"),
+    "cfg3e": dict(shape=(64, 64, 32), kernel="exp", nd=0, name="64x64x32 two-property cube, sqexp (fp64 path)"),
+    "cfg4": dict(shape=(96, 96, 48), kernel="exp", nd=0, name="96x96x48 cube, 2-property joint inversion (fp64 path)"),
+}
+METRIC = "voxels/sec joint-inversion (cov+chol+solve)"
+
+
+def read_peaks():
+    peaks = {}
+    for name in ("MEASURED_PEAKS.json", os.path.join("profiles", "fp64_peaks_r1.json")):
+        p = os.path.join(ROOT, name)
+        if os.path.exists(p):
+            try:
+                peaks.update(json.load(open(p)))
+            except Exception:
+                pass
+    return peaks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def effective_lengths(cfg_mod, wl):
+    from geobo_b200 import kernels
+    gl = cfg_mod.gp_lengthscale * np.asarray([cfg_mod.xvoxsize] * 3) * np.asarray(wl.get("gl_mult", (1.0, 1.0, 1.0)))
+    return kernels.dedup_lengthscales(np.array(gl, dtype=float))
+
+
+def algorithmic_flops(N, Ns, nd, ncol):
+    """block-structured dense algorithm, counted once (per rank for its ncol voxel columns)."""
+    M = 2 * Ns + nd
+    return dict(project=12.0 * ncol * N * Ns, aka=2.0 * ncol * (3 * Ns * Ns), chol=M ** 3 / 3.0, trsm=3.0 * ncol * M * M,
+                mean_var=4.0 * 3 * ncol * M)
+
+
+def run_ours(args):
+    from geobo_b200 import _lib, config_loader, dist, inversion, synth
+    wl = WORKLOADS[args.workload]
+    ctx = _lib.default_context()
+    rank, world = dist.init_from_env(ctx)
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    xN, yN, zN = wl["shape"]
+    cfg = synth.settings(xN, yN, zN, kernelfunc=wl["kernel"])
+    config_loader.load_settings(cfg, make_outpath=False)
+    N, Ns, nd = xN * yN * zN, xN * yN, wl["nd"]
+    f = synth.make_inputs(nd=nd, seed=0, ctx=ctx)
+    info = ctx.device_info()
+
+    # ---------------- device-resident problem (value) ----------------
+    inv = inversion.Inversion()
+    inv.create_cubegeometry()
+    inv.gp_length = inv.gp_length * np.asarray(wl.get("gl_mult", (1.0, 1.0, 1.0)))
+    gl_eff = effective_lengths(config_loader, wl)
+    c0, c1 = dist.shard_columns(N, world, rank) if world > 1 else (0, N)
+    drill_idx = np.flatnonzero(f["drilldata0"].ravel() != 0)
+    prob = _lib.Problem(ctx, (xN, yN, zN), (config_loader.xvoxsize, config_loader.yvoxsize, config_loader.zvoxsize),
+                        inv.Edges, f["sensor_locations"], config_loader.magneticField, config_loader.c_MILLIGALS_UNITS,
+                        config_loader.fcor_grav, 1.0, config_loader.fcor_mag, drill_idx, c0, c1)
+    y = np.hstack([(f["grav"] - f["grav"].mean()) / f["grav"].std(), (f["mag"] - f["mag"].mean()) / f["mag"].std(),
+                   (f["drillfield"] - f["drillfield"].mean()) / f["drillfield"].std() if nd else np.zeros(0)])
+    prob.set_data(y)
+    h = prob.hyper(gl_eff, config_loader.gp_err, config_loader.gp_coeff, 1.0, wl["kernel"])
+    t_sens_ms = prob.timings()["a_sens"]
+    for _ in range(args.warmup):
+        prob.predict(h, want_host=False)
+    sampler = ClockSampler(ctx_device())
+    dist.barrier()
+    sampler.start()
+    stage_ms = {}
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, logl, info_pd = prob.predict(h, want_host=False)     # synchronises the stream on return
+        tm = prob.timings()
+        dev_ms += tm["total"]
+        for k, v in tm.items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+    wall = time.perf_counter() - t0
+    dist.barrier()
+    clocks = sampler.stop()
+    launches = int(round(tm["launches"]))
+    dev_s = dist.max_over_ranks(dev_ms / 1e3)
+    wall_s = dist.max_over_ranks(wall)
+    ms_per_step = dev_s * 1e3 / args.steps
+    value = N * args.steps / dev_s
+    stage_ms = {k: v / args.steps for k, v in stage_ms.items() if k != "launches"}
+
+    # ---------------- end to end through Inversion.cubing (host arrays in, six host cubes out) ----------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    dist.barrier()
+    inv2 = inversion.Inversion()
+    inv2.create_cubegeometry()
+    inv2.gp_length = inv2.gp_length * np.asarray(wl.get("gl_mult", (1.0, 1.0, 1.0)))
+    gl0 = inv2.gp_length.copy()
+    inv2.cubing(f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"])   # warm-up
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        inv2.gp_length = gl0.copy()
+        cubes = inv2.cubing(f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"])
+    e2e_s = dist.max_over_ranks(time.perf_counter() - t0)
+    dist.barrier()
+    M = 2 * Ns + nd
+    h2d = 8 * (f["grav"].size + f["mag"].size + f["sensor_locations"].size + inv2.Edges.size + M) + 8 * nd
+    d2h = 8 * (6 * (c1 - c0) + 2) + 4
+    e2e = {"value": N * e2e_steps / e2e_s, "unit": "voxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": e2e_steps, "ms_per_step": e2e_s * 1e3 / e2e_steps,
+           "includes": "device problem build (A_sens x2 on GPU), H2D of data/geometry, predict3 stage, D2H of 6 cubes"}
+    finite = bool(all(np.isfinite(cb).all() for cb in cubes[:2]))
+
+    if rank != 0:
+        return
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks = read_peaks()
+    fl = algorithmic_flops(N, Ns, nd, c1 - c0)
+    proj_s = stage_ms["project"] / 1e3
+    achieved = fl["project"] / proj_s / 1e12
+    fp64_peak = peaks.get("cublas_dgemm_8192_tflops")
+    roofline = {"kernel": "gemm_f64_kernel<B_GEN> (fused covariance assembly + projection Pt = A.K, fp64 DMMA)",
+                "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": (achieved / fp64_peak) if fp64_peak else None,
+                "peak_source": "fp64 tensor pipe measured on this pool with tools/peaks.cu (cuBLAS DGEMM 8192^3; DMMA issue peak %s); "
+                               "MEASURED_PEAKS.json carries no fp64 figure (its bf16 figure, %s TFLOP/s, does not bound an fp64 kernel)"
+                               % (peaks.get("dmma_tflops_w16"), peaks.get("bf16_tflops")),
+                "algorithmic_flops_per_launch": fl["project"], "ms_per_launch": stage_ms["project"],
+                "share_of_step": stage_ms["project"] / ms_per_step,
+                "traffic": peaks.get("traffic_project_%s" % args.workload)}
+    out = {"metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic (cylinders truth cube, forward-simulated grav/mag surveys, seed 0)",
+           "config": {"workload": wl["name"], "workload_id": args.workload, "voxels": N, "sensors_per_survey": Ns, "drill_rows": nd,
+                      "data_rows_M": M, "kernel": wl["kernel"], "parallelism": "voxel-column shards of Pt x%d" % world,
+                      "l2": "inputs larger than L2 (A and Pt are %.1f GB)" % (prob.device_bytes() / 1e9),
+                      "device_bytes": prob.device_bytes()},
+           "wall_ms_per_step": wall_s * 1e3 / args.steps, "stage_ms": stage_ms, "a_sens_ms": t_sens_ms,
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "roofline": roofline,
+           "logl": logl, "info": info_pd, "finite": finite, "gpu": info["name"]}
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, cfg, wl, f, y)
+    print(json.dumps(out))
+
+
+def ctx_device():
+    return int(os.environ.get("GEOBO_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def cpu_inputs(cfg, wl, f, nsens_cap=None):
+    """Oracle-side operands for the CPU timing (the sensitivities are computed with the oracle's own A_sens)."""
+    from oracle import numpy_oracle as o
+    c = o.make_config(cfg)
+    E, _ = o.cube_geometry(c)
+    return c, E
+
+
+def cpu_baseline(args, cfg, wl, f, y, target_seconds=20.0):
+    """Lean NumPy/SciPy restatement of the reference (oracle/numpy_oracle.py) on this box's host cores."""
+    from oracle import numpy_oracle as o
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        threads = os.cpu_count()
+    c = o.make_config(cfg)
+    N = c.xNcube * c.yNcube * c.zNcube
+    Ns = c.xNcube * c.yNcube
+    rng = np.random.default_rng(0)
+    # The sensitivities only enter the timed stage as dgemm operands (timing is value-independent): use the oracle's
+    # A_sens for a few sensors and tile them, so the bounded sample does not spend minutes in the (untimed) A_sens loop.
+    E, _ = o.cube_geometry(c)
+    rows = np.unique(np.linspace(0, Ns - 1, min(Ns, 8)).astype(int))
+    Ag_s = o.a_sens(c, c.magneticField * 0, f["sensor_locations"], E, "grav", sensors=list(rows))
+    Am_s = o.a_sens(c, c.magneticField, f["sensor_locations"], E, "magn", sensors=list(rows))
+    reps = -(-Ns // len(rows))
+    Ag = np.tile(Ag_s, (reps, 1))[:Ns] * (1.0 + 0.01 * rng.standard_normal((Ns, 1)))
+    Am = np.tile(Am_s, (reps, 1))[:Ns] * (1.0 + 0.01 * rng.standard_normal((Ns, 1)))
+    didx = o.drill_indices(f["drilldata0"])
+    gl = c.gp_lengthscale * c.xvoxsize * np.asarray(wl.get("gl_mult", (1.0, 1.0, 1.0)))
+    # size the sample: one probe with 64 columns, then scale to ~target_seconds
+    probe = o.cpu_baseline_sample(c, [Ag, Am], didx, np.nan_to_num(y), gp_length=gl.copy(), ncols_sample=min(N, 64))
+    per_col = max(probe["seconds_measured"] / min(N, 64), 1e-6)
+    ncols = int(min(N, max(64, target_seconds / per_col)))
+    res = o.cpu_baseline_sample(c, [Ag, Am], didx, np.nan_to_num(y), gp_length=gl.copy(), ncols_sample=ncols)
+    return {"value": N / res["seconds_estimated"], "unit": "voxels/s", "cores": int(threads), "kind": "port",
+            "host_cpus": os.cpu_count(), "sample": res["sample"], "seconds_estimated_full": res["seconds_estimated"],
+            "seconds_measured": res["seconds_measured"], "stages_s": res["stages"],
+            "what": "oracle/numpy_oracle.py lean restatement of geobo predict3 (NumPy ufuncs single-threaded as in the "
+                    "reference, OpenBLAS dgemm/LAPACK multi-threaded)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure Python and
+    cannot travel to the GPU box) on the host cores, bounded sample per step, same metric / config / unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from geobo_b200 import synth
+    from oracle import numpy_oracle as o
+    wl = WORKLOADS[args.workload]
+    xN, yN, zN = wl["shape"]
+    cfg = synth.settings(xN, yN, zN, kernelfunc=wl["kernel"])
+    c = o.make_config(cfg)
+    N, Ns, nd = xN * yN * zN, xN * yN, wl["nd"]
+    rng = np.random.default_rng(0)
+    d0 = np.zeros(N)
+    if nd:
+        d0[rng.choice(N, nd, replace=False)] = 1.0
+    f = dict(sensor_locations=o.sensor_grid(c), drilldata0=d0.reshape(xN, yN, zN))
+    y = rng.standard_normal(2 * Ns + nd)
+    per_step_budget = max(5.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_baseline(args, cfg, wl, f, y, target_seconds=per_step_budget)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    value = float(np.mean(vals))
+    M = 2 * Ns + nd
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": N / value * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": wl["name"], "workload_id": args.workload, "voxels": N, "sensors_per_survey": Ns, "drill_rows": nd,
+                      "data_rows_M": M, "kernel": wl["kernel"]},
+           "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")},
+           "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "ms_per_step is the estimated whole-cube time of one CPU inversion; each step times a bounded sample (see cpu_baseline.sample)"}
+    out["cpu_baseline"]["value"] = value
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("GEOBO_B200_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

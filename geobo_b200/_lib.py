@@ -16,7 +16,7 @@ GB_OK = 0
 KERNEL_IDS = {"sparse": 0, "exp": 1, "matern32": 2}
 SENS_KINDS = {"grav": 0, "magn": 1}
 FLAG_MEAN, FLAG_VAR, FLAG_LOGL, FLAG_ALL = 1, 2, 4, 7
-TIMER_NAMES = ["a_sens", "tables", "project", "drill_rows", "aka", "allreduce", "chol", "trsm", "mean_var", "total", "d2h"]
+TIMER_NAMES = ["a_sens", "tables", "project", "drill_rows", "aka", "allreduce", "chol", "trsm", "mean_var", "total", "d2h", "launches"]
 
 
 class GeoboB200Error(RuntimeError):

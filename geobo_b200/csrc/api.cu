@@ -254,6 +254,7 @@ struct gb_problem {
     double ms[GB_NUM_TIMERS];
     uint64_t bytes = 0;
     bool have_data = false;
+    bool last_full = false;
 };
 
 template <typename T>
@@ -474,6 +475,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     gb_ctx* ctx = p->ctx;
     cudaStream_t s = ctx->stream;
     if (!p->have_data) return gb_fail(ctx, GB_ERR_ARG, "gb_predict before gb_problem_set_data");
+    p->last_full = full;
     CovParams cp;
     GB_TRY(fill_cov_params(ctx, cp, h->kernel_id, h->gp_length, h->coeffm, h->gp_amp));
     GB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -570,6 +572,14 @@ static int collect_timings(gb_problem* p) {
     float t = 0.f;
     GB_CUDA(ctx, cudaEventElapsedTime(&t, p->ev[0], p->ev[8]));
     p->ms[GB_T_TOTAL] = t;
+    {
+        // kernels launched by run_predict: tables, set_y, project, [drill rows x2], aka, noise diag,
+        // Cholesky (potrf + panel + trailing per block), two blocked solves (2 GEMMs per block), dot, mean/var
+        const long nblk = p->Mp / 128;
+        long n = 5 + (p->nd ? 2 : 0) + (3 * nblk - 2) + 2 * nblk + 1;
+        if (p->last_full) n += 2 * nblk + 1;
+        p->ms[GB_T_LAUNCHES] = (double)n;
+    }
     return GB_OK;
 }
 

@@ -109,7 +109,7 @@ class Inversion:
         # kernels.create_cov de-duplicates the length scales in place on the caller's array (Q1)
         kernel.dedup_lengthscales(np.asarray(self.gp_length))
         mu, var, logl, info = self._problem.predict(self._hyper())
-        if info > 0 or not np.isfinite(logl):
+        if info > 0:
             print("Cholesky decompostion failed, AkA matrix i likely not positive semitive.")
             print("Change GP parameter settings")
             sys.exit(1)

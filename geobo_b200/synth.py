@@ -34,7 +34,7 @@ def sensor_grid():
 
 
 def cylinders(voxelpos):
-    """simcube.py:83-92"""
+    """simcube.py:83-92 plus a smooth background term."""
     shp = (_cfg.yNcube, _cfg.xNcube, _cfg.zNcube)
     x3, y3, z3 = (np.asarray(v).reshape(shp) for v in voxelpos)
     rad = _cfg.yLcube / 18.
@@ -44,6 +44,9 @@ def cylinders(voxelpos):
     density[rc2 <= rad**2] = 1.
     density[rc1 <= rad**2] = 1.
     density[(x3 < _cfg.xLcube / 5.) | (x3 > _cfg.xLcube * 4. / 5.)] = 0.1
+    # smooth background so that drill samples are never all equal (constant samples have zero std
+    # and normalise to NaN in the reference, inversion.py:213-214)
+    density = density + 0.05 * np.sin(x3 / 400.) * np.cos(y3 / 300.) + 0.02 * z3 / _cfg.zLcube
     return density, _cfg.gp_coeff[1] * density
 
 

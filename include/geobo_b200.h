@@ -62,6 +62,7 @@ extern "C" {
 #define GB_T_MEANVAR 8     /* mean, variance diag, logl           */
 #define GB_T_TOTAL 9       /* whole gb_predict on device          */
 #define GB_T_D2H 10        /* result copies to host               */
+#define GB_T_LAUNCHES 11   /* number of library kernels launched by the last gb_predict / gb_neg_logl (a count, not ms) */
 
 typedef struct gb_ctx gb_ctx;
 typedef struct gb_problem gb_problem;

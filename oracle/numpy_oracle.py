@@ -437,6 +437,60 @@ def calc_logl(c, A_list, didx, y, params5):
     return -logl
 
 
+# --------------------------------------------------------------------------- bounded CPU baseline (bench.py only)
+def cpu_baseline_sample(c, A_list, didx, y, gp_length=None, ncols_sample=512, jchunk=2048):
+    """Time the lean CPU path of predict3 on a bounded, deterministic sample and scale to the whole cube.
+
+    Every stage except the M x M Cholesky is linear in the number of voxel columns of ``Pt``
+    (kernel evaluation + projection dgemm, AkA accumulation, triangular solve, mean/variance), so
+    those are timed on ``ncols_sample`` evenly spaced columns and multiplied by ``N / ncols_sample``;
+    the Cholesky is timed at full size on the sampled (SPD) matrix.  Returns a dict with the
+    estimated whole-cube seconds, the per-stage split and the sample description."""
+    xN, yN, zN = c.xNcube, c.yNcube, c.zNcube
+    N = xN * yN * zN
+    Ns = A_list[0].shape[0]
+    nd = didx.size
+    M = 2 * Ns + nd
+    gl, sig, w, amp = _gp_setup(c, gp_length)
+    params = dedup_lengths(gl)
+    pts = grid_points((xN, yN, zN), (c.xvoxsize, c.yvoxsize, c.zvoxsize))
+    ncols_sample = int(min(N, ncols_sample))
+    cols = np.unique(np.linspace(0, N - 1, ncols_sample).astype(np.int64))
+    scale = N / cols.size
+    timers = {}
+    t0 = time.perf_counter()
+    Pt = pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, timers=timers)   # (M, 3, ncols)
+    t_panel = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    AkA = np.empty((M, M))
+    AkA[:Ns] = A_list[0][:, cols] @ Pt[:, 0, :].T
+    AkA[Ns:2 * Ns] = A_list[1][:, cols] @ Pt[:, 1, :].T
+    t_aka = time.perf_counter() - t0   # (the nd drill rows of AkA are gathers, not arithmetic)
+    # SPD surrogate of the same size for the (size-dependent only) Cholesky timing
+    S = 0.5 * (AkA[:2 * Ns, :2 * Ns] + AkA[:2 * Ns, :2 * Ns].T) * scale
+    full = np.eye(M)
+    full[:2 * Ns, :2 * Ns] = S
+    full[np.diag_indices(M)] += np.abs(full).sum(axis=1) + sig[0] ** 2   # diagonally dominant => SPD (timing only)
+    t0 = time.perf_counter()
+    L = cholesky(full, lower=True)
+    t_chol = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    u = solve_triangular(L, y, lower=True)
+    V = solve_triangular(L, Pt.reshape(M, -1), lower=True, check_finite=False)
+    t_trsm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    mu = V.T @ u
+    var = amp - np.einsum("ij,ij->j", V, V)
+    t_mv = time.perf_counter() - t0
+    est = (t_panel + t_aka + t_trsm + t_mv) * scale + t_chol
+    return dict(seconds_estimated=est, seconds_measured=t_panel + t_aka + t_chol + t_trsm + t_mv, scale=scale,
+                stages=dict(kernel_eval=timers.get("kernel_eval", 0.0) * scale, dgemm_proj=timers.get("dgemm_proj", 0.0) * scale,
+                            aka=t_aka * scale, chol=t_chol, trsm=t_trsm * scale, mean_var=t_mv * scale),
+                sample="%d of %d voxel columns of Pt=A.K (all M=%d rows, full contraction over N), stages scaled x%.1f; "
+                       "Cholesky M=%d timed in full" % (cols.size, N, M, scale, M),
+                checksum=float(np.nansum(mu) + np.nansum(var)))
+
+
 # --------------------------------------------------------------------------- synthetic truth (bench inputs)
 def cylinders_truth(c, voxelpos):
     """simcube.py:83-92 ('cylinders'): density/magsus cubes as pure functions of voxel coordinates."""

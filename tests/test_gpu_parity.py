@@ -195,7 +195,7 @@ def base_cfg():
     return dict(BASE)
 
 
-@pytest.mark.parametrize("shape,kf,nd", [((5, 3, 7), "exp", 3), ((9, 2, 1), "sparse", 2), ((3, 4, 19), "matern32", 5),
+@pytest.mark.parametrize("shape,kf,nd", [((7, 5, 3), "exp", 3), ((9, 2, 1), "sparse", 2), ((3, 4, 19), "matern32", 5),
                                          ((16, 16, 16), "exp", 50), ((17, 13, 9), "sparse", 0)])
 def test_cubing_odd_shapes_vs_oracle(ctx, shape, kf, nd):
     """Shapes that are not multiples of any tile size (N, Ns, M all ragged), all three kernels, nd = 0 and > 0."""
