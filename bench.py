@@ -260,11 +260,7 @@ def cpu_baseline(args, cfg, wl, f, y, target_seconds=20.0):
     Am = np.tile(Am_s, (reps, 1))[:Ns] * (1.0 + 0.01 * rng.standard_normal((Ns, 1)))
     didx = o.drill_indices(f["drilldata0"])
     gl = c.gp_lengthscale * c.xvoxsize * np.asarray(wl.get("gl_mult", (1.0, 1.0, 1.0)))
-    # size the sample: one probe with 64 columns, then scale to ~target_seconds
-    probe = o.cpu_baseline_sample(c, [Ag, Am], didx, np.nan_to_num(y), gp_length=gl.copy(), ncols_sample=min(N, 64))
-    per_col = max(probe["seconds_measured"] / min(N, 64), 1e-6)
-    ncols = int(min(N, max(64, target_seconds / per_col)))
-    res = o.cpu_baseline_sample(c, [Ag, Am], didx, np.nan_to_num(y), gp_length=gl.copy(), ncols_sample=ncols)
+    res = o.cpu_baseline_sample(c, [Ag, Am], didx, np.nan_to_num(y), gp_length=gl.copy(), target_seconds=target_seconds)
     return {"value": N / res["seconds_estimated"], "unit": "voxels/s", "cores": int(threads), "kind": "port",
             "host_cpus": os.cpu_count(), "sample": res["sample"], "seconds_estimated_full": res["seconds_estimated"],
             "seconds_measured": res["seconds_measured"], "stages_s": res["stages"],

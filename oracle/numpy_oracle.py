@@ -313,8 +313,9 @@ def drill_indices(drilldata0):
     return np.flatnonzero(np.asarray(drilldata0).ravel() != 0)
 
 
-def pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=2048, timers=None):
+def pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=2048, timers=None, jstarts=None):
     """Columns ``cols`` (voxel indices i) of Pt = Asens3 . kcov for all three property blocks r.
+    ``jstarts``: optional subset of contraction chunks (bounded timing samples only; result then partial).
 
     Returns array (M, 3, len(cols)):  Pt[(cb, s), r, i] = sum_j A_cb[s, j] * K[(cb, j), (r, i)].
     """
@@ -327,7 +328,7 @@ def pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=2048, timers=Non
     fk = c.kernelfunc
     for cb in range(2):
         A = A_list[cb]
-        for j0 in range(0, N, jchunk):
+        for j0 in (range(0, N, jchunk) if jstarts is None else jstarts):
             J = np.arange(j0, min(N, j0 + jchunk))
             t0 = time.perf_counter()
             # D2[j, i] for j in J (rows), i in cols: same arithmetic as sqdist()
@@ -438,14 +439,15 @@ def calc_logl(c, A_list, didx, y, params5):
 
 
 # --------------------------------------------------------------------------- bounded CPU baseline (bench.py only)
-def cpu_baseline_sample(c, A_list, didx, y, gp_length=None, ncols_sample=512, jchunk=2048):
+def cpu_baseline_sample(c, A_list, didx, y, gp_length=None, panel_cols=2048, jchunk=2048, n_jchunks=None, target_seconds=20.0):
     """Time the lean CPU path of predict3 on a bounded, deterministic sample and scale to the whole cube.
 
-    Every stage except the M x M Cholesky is linear in the number of voxel columns of ``Pt``
-    (kernel evaluation + projection dgemm, AkA accumulation, triangular solve, mean/variance), so
-    those are timed on ``ncols_sample`` evenly spaced columns and multiplied by ``N / ncols_sample``;
-    the Cholesky is timed at full size on the sampled (SPD) matrix.  Returns a dict with the
-    estimated whole-cube seconds, the per-stage split and the sample description."""
+    The projection Pt = A.K costs the same for every (column panel, contraction chunk) pair, so it is
+    timed on ONE panel of ``panel_cols`` voxel columns x ``n_jchunks`` evenly spaced contraction chunks of
+    ``jchunk`` voxels (BLAS-efficient shapes, like the full run) and scaled by the pair count.  AkA,
+    the triangular solve and mean/variance are linear in the column count: timed on the panel and
+    scaled by N / panel_cols.  The M x M Cholesky is timed in full on an SPD matrix of the true size.
+    Returns the estimated whole-cube seconds, the per-stage split and the sample description."""
     xN, yN, zN = c.xNcube, c.yNcube, c.zNcube
     N = xN * yN * zN
     Ns = A_list[0].shape[0]
@@ -454,22 +456,30 @@ def cpu_baseline_sample(c, A_list, didx, y, gp_length=None, ncols_sample=512, jc
     gl, sig, w, amp = _gp_setup(c, gp_length)
     params = dedup_lengths(gl)
     pts = grid_points((xN, yN, zN), (c.xvoxsize, c.yvoxsize, c.zvoxsize))
-    ncols_sample = int(min(N, ncols_sample))
-    cols = np.unique(np.linspace(0, N - 1, ncols_sample).astype(np.int64))
-    scale = N / cols.size
+    panel_cols = int(min(N, panel_cols))
+    cols = np.arange((N - panel_cols) // 2, (N - panel_cols) // 2 + panel_cols)
+    all_j = list(range(0, N, jchunk))
+    if n_jchunks is None:
+        # probe one chunk, then take as many as fit the time budget (the non-projection stages take a share too)
+        t0 = time.perf_counter()
+        pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=all_j[:1])
+        per = max(time.perf_counter() - t0, 1e-3)
+        n_jchunks = int(max(1, min(len(all_j), 0.6 * target_seconds / per)))
+    sel = [all_j[i] for i in np.unique(np.linspace(0, len(all_j) - 1, n_jchunks).astype(int))]
     timers = {}
     t0 = time.perf_counter()
-    Pt = pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, timers=timers)   # (M, 3, ncols)
+    Pt = pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, timers=timers, jstarts=sel)   # (M, 3, panel)
     t_panel = time.perf_counter() - t0
+    scale_cols = N / panel_cols
+    scale_proj = scale_cols * (len(all_j) / len(sel))
     t0 = time.perf_counter()
     AkA = np.empty((M, M))
     AkA[:Ns] = A_list[0][:, cols] @ Pt[:, 0, :].T
     AkA[Ns:2 * Ns] = A_list[1][:, cols] @ Pt[:, 1, :].T
     t_aka = time.perf_counter() - t0   # (the nd drill rows of AkA are gathers, not arithmetic)
-    # SPD surrogate of the same size for the (size-dependent only) Cholesky timing
-    S = 0.5 * (AkA[:2 * Ns, :2 * Ns] + AkA[:2 * Ns, :2 * Ns].T) * scale
+    # SPD surrogate of the true size for the (size-dependent only) Cholesky timing
     full = np.eye(M)
-    full[:2 * Ns, :2 * Ns] = S
+    full[:2 * Ns, :2 * Ns] = 0.5 * (AkA[:2 * Ns, :2 * Ns] + AkA[:2 * Ns, :2 * Ns].T)
     full[np.diag_indices(M)] += np.abs(full).sum(axis=1) + sig[0] ** 2   # diagonally dominant => SPD (timing only)
     t0 = time.perf_counter()
     L = cholesky(full, lower=True)
@@ -482,12 +492,13 @@ def cpu_baseline_sample(c, A_list, didx, y, gp_length=None, ncols_sample=512, jc
     mu = V.T @ u
     var = amp - np.einsum("ij,ij->j", V, V)
     t_mv = time.perf_counter() - t0
-    est = (t_panel + t_aka + t_trsm + t_mv) * scale + t_chol
-    return dict(seconds_estimated=est, seconds_measured=t_panel + t_aka + t_chol + t_trsm + t_mv, scale=scale,
-                stages=dict(kernel_eval=timers.get("kernel_eval", 0.0) * scale, dgemm_proj=timers.get("dgemm_proj", 0.0) * scale,
-                            aka=t_aka * scale, chol=t_chol, trsm=t_trsm * scale, mean_var=t_mv * scale),
-                sample="%d of %d voxel columns of Pt=A.K (all M=%d rows, full contraction over N), stages scaled x%.1f; "
-                       "Cholesky M=%d timed in full" % (cols.size, N, M, scale, M),
+    est = t_panel * scale_proj + (t_aka + t_trsm + t_mv) * scale_cols + t_chol
+    return dict(seconds_estimated=est, seconds_measured=t_panel + t_aka + t_chol + t_trsm + t_mv,
+                stages=dict(kernel_eval=timers.get("kernel_eval", 0.0) * scale_proj, dgemm_proj=timers.get("dgemm_proj", 0.0) * scale_proj,
+                            aka=t_aka * scale_cols, chol=t_chol, trsm=t_trsm * scale_cols, mean_var=t_mv * scale_cols),
+                sample="projection Pt=A.K timed on 1 panel of %d voxel columns x %d of %d contraction chunks of %d voxels (all %d "
+                       "sensor rows), scaled x%.1f; AkA / triangular solve / mean+variance timed on that panel, scaled x%.1f; "
+                       "Cholesky M=%d timed in full" % (panel_cols, len(sel), len(all_j), jchunk, 2 * Ns, scale_proj, scale_cols, M),
                 checksum=float(np.nansum(mu) + np.nansum(var)))
 
 

@@ -212,7 +212,7 @@ def test_cubing_odd_shapes_vs_oracle(ctx, shape, kf, nd):
 
 def test_not_positive_definite_exits_like_reference(ctx, capsys):
     """matern32 with equal scales: 0/0 in the cross term -> Cholesky fails -> two prints + sys.exit(1) (inversion.py:99-104)."""
-    c = configure(base_cfg(), xNcube=4, yNcube=3, zNcube=2, kernelfunc="matern32")
+    c = configure(base_cfg(), xNcube=6, yNcube=5, zNcube=4, kernelfunc="matern32")
     f = synthetic_inputs(c, 2)
     with pytest.raises(SystemExit) as e:
         run_cubing(f)
