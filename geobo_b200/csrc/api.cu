@@ -308,8 +308,8 @@ extern "C" int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* d, gb_probl
     p->ctx = ctx;
     for (int i = 0; i < 3; ++i) { p->n[i] = d->ncube[i]; p->vox[i] = d->voxsize[i]; }
     p->N = N; p->Ns = d->nsens; p->nd = d->ndrill; p->M = 2 * p->Ns + p->nd; p->Mp = round_up(p->M, 128);
-    p->c0 = c0; p->c1 = c1; p->ncol = c1 - c0; p->ncp = round_up(p->ncol, 16); p->ldp = 3 * p->ncp;
-    p->Kp = round_up(N, 16); p->lda = p->Kp + 16;
+    p->c0 = c0; p->c1 = c1; p->ncol = c1 - c0; p->ncp = round_up(p->ncol, 32); p->ldp = 3 * p->ncp;
+    p->Kp = round_up(N, 32); p->lda = p->Kp + 32;   // multiples of the largest GEMM slab (BK = 32)
     p->ext = (2 * xN - 1) * (2 * yN - 1) * (2 * zN - 1);
     p->C0 = ((yN - 1) * (2 * xN - 1) + (xN - 1)) * (2 * zN - 1) + (zN - 1);
     p->drill.assign(d->drill_idx, d->drill_idx + d->ndrill);

@@ -12,68 +12,121 @@ constexpr int NB = 128;
 constexpr int PLD = NB + 1;   // padded leading dimension in shared memory
 
 // Factor one 128x128 diagonal block in place (lower), write its inverse to linv (row-major, upper zero).
+//
+// Register-tiled right-looking Cholesky: 256 threads as a 16 x 16 grid, thread (ty, tx) owns the 8 x 8
+// cyclic sub-matrix {(ty + 16a, tx + 16b)} of the (symmetric) block in registers; per pivot k the owner
+// publishes sqrt(d), the owners of column k publish the scaled column through shared memory, and every
+// thread applies the rank-1 update to its registers (2 barriers per pivot, no shared-memory matrix traffic).
+// The inverse of the factor (used for the panel solve and the blocked forward substitution) is then
+// built column by column with two lanes per column.
 __global__ void __launch_bounds__(256, 1) potrf128_kernel(double* __restrict__ Bm, long ldb, int k0, int Mtrue,
                                                           double* __restrict__ linv, double* __restrict__ logdet,
                                                           int* __restrict__ info) {
-    extern __shared__ double S[];   // [NB][PLD]; lower = L, strict upper = X^T (inverse), xd = diag of inverse
+    extern __shared__ double S[];   // [NB][PLD]; lower = L, strict upper = X^T (inverse)
+    __shared__ double colk[NB];
     __shared__ double xd[NB];
+    __shared__ double red[NB];
+    __shared__ double pivs;
     __shared__ int bad;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     double* blk = Bm + (long)k0 * ldb + k0;
+    double reg[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            reg[a][b] = (c <= r) ? blk[(long)r * ldb + c] : blk[(long)c * ldb + r];   // only the lower triangle is valid in memory
+        }
     if (tid == 0) bad = 0;
-    for (int e = tid; e < NB * NB; e += blockDim.x) {
-        const int r = e / NB, c = e % NB;
-        S[r * PLD + c] = (c <= r) ? blk[(long)r * ldb + c] : 0.0;
-    }
     __syncthreads();
-    for (int k = 0; k < NB; ++k) {
-        if (tid == 0) {
-            const double d = S[k * PLD + k];
-            if (!(d > 0.0) && bad == 0) bad = k0 + k + 1;
-            S[k * PLD + k] = sqrt(d);
-        }
-        __syncthreads();
-        const double piv = S[k * PLD + k];
-        for (int r = k + 1 + tid; r < NB; r += blockDim.x) S[r * PLD + k] = S[r * PLD + k] / piv;
-        __syncthreads();
-        // trailing update of the lower triangle: element (r, c), k < c <= r
-        const int rem = NB - 1 - k;
-        for (int e = tid; e < rem * rem; e += blockDim.x) {
-            const int r = k + 1 + e / rem, c = k + 1 + e % rem;
-            if (c <= r) S[r * PLD + c] -= S[r * PLD + k] * S[c * PLD + k];
-        }
-        __syncthreads();
-    }
-    // inverse of the triangular block: thread c owns column c of X = L^-1, stored transposed in the upper half
-    if (tid < NB) {
-        const int c = tid;
-        const double xc = 1.0 / S[c * PLD + c];
-        xd[c] = xc;
-        for (int r = c + 1; r < NB; ++r) {
-            double s0 = S[r * PLD + c] * xc, s1 = 0.0;
-            int k = c + 1;
-            for (; k + 1 < r; k += 2) {
-                s0 = fma(S[r * PLD + k], S[c * PLD + k], s0);
-                s1 = fma(S[r * PLD + k + 1], S[c * PLD + k + 1], s1);
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = kb * 16 + kk;
+            if (ty == kk && tx == kk) {
+                const double d = reg[kb][kb];
+                if (!(d > 0.0) && bad == 0) bad = k0 + k + 1;
+                pivs = sqrt(d);
             }
-            if (k < r) s0 = fma(S[r * PLD + k], S[c * PLD + k], s0);
-            S[c * PLD + r] = -(s0 + s1) / S[r * PLD + r];
+            __syncthreads();
+            const double piv = pivs;
+            if (tx == kk) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const int r = ty + 16 * a;
+                    if (r >= k) {
+                        const double l = (r == k) ? piv : reg[a][kb] / piv;
+                        colk[r] = l;
+                        reg[a][kb] = l;
+                    }
+                }
+            }
+            __syncthreads();
+            double lr[8], lc[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) lr[a] = colk[ty + 16 * a];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) lc[b] = colk[tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b)
+                    if (ty + 16 * a > k && tx + 16 * b > k) reg[a][b] -= lr[a] * lc[b];
+        }
+    }
+    // publish L (lower) to shared memory and to the matrix
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            if (c <= r) {
+                S[r * PLD + c] = reg[a][b];
+                blk[(long)r * ldb + c] = reg[a][b];
+            }
+        }
+    __syncthreads();
+    // X = L^-1, column c by the lane pair (2c, 2c+1); X^T goes to the strict upper triangle of S
+    {
+        const int c = tid >> 1, h = tid & 1;
+        const int cmin = (tid & ~31) >> 1;          // smallest column handled by this warp: uniform loop bounds
+        const double xc = 1.0 / S[c * PLD + c];
+        if (h == 0) xd[c] = xc;
+        for (int r = cmin + 1; r < NB; ++r) {
+            double s0 = 0.0, s1 = 0.0;
+            if (r > c) {
+                int k = c + h;
+                if (k == c && k < r) { s0 = S[r * PLD + c] * xc; k += 2; }
+                for (; k + 2 < r; k += 4) {
+                    s0 = fma(S[r * PLD + k], S[c * PLD + k], s0);
+                    s1 = fma(S[r * PLD + k + 2], S[c * PLD + k + 2], s1);
+                }
+                for (; k < r; k += 2) s0 = fma(S[r * PLD + k], S[c * PLD + k], s0);
+            }
+            double tot = s0 + s1;
+            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+            if (r > c && h == 0) S[c * PLD + r] = -tot / S[r * PLD + r];
+            __syncwarp();
         }
     }
     __syncthreads();
     for (int e = tid; e < NB * NB; e += blockDim.x) {
-        const int r = e / NB, c = e % NB;
-        if (c <= r) blk[(long)r * ldb + c] = S[r * PLD + c];
+        const int r = e >> 7, c = e & (NB - 1);
         linv[e] = (c < r) ? S[c * PLD + r] : (c == r ? xd[r] : 0.0);
     }
+    // log det: fixed-order tree reduction (deterministic)
+    if (tid < NB) {
+        const double l = S[tid * PLD + tid];
+        red[tid] = (k0 + tid < Mtrue) ? log(l * l) : 0.0;     // inversion.py:108: log(diag(L)**2)
+    }
+    __syncthreads();
+    for (int o = NB / 2; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
     if (tid == 0) {
-        double ld = 0.0;
-        for (int k = 0; k < NB; ++k)
-            if (k0 + k < Mtrue) {
-                const double l = S[k * PLD + k];
-                ld += log(l * l);                     // inversion.py:108: log(diag(L)**2)
-            }
-        *logdet += ld;
+        *logdet += red[0];
         if (bad && *info == 0) *info = bad;
     }
 }

@@ -5,19 +5,25 @@
 //     memory from the stationary-covariance table -- the 3N x 3N matrix never exists in HBM),
 //   * AkA = A . Pt^T, the Cholesky panel / trailing updates, and the blocked triangular solve.
 //
-// CTA tile 128 x 128 x 16, 8 warps (2 x 4), warp tile 64 x 32 = 8 x 4 DMMA fragments,
-// 3-stage cp.async (LDGSTS) pipeline, 16-byte copies for stored operands and 8-byte
+// CTA tile 128 x 128 x BK, 8 warps (2 x 4), warp tile 64 x 32 = 8 x 4 DMMA fragments,
+// multi-stage cp.async (LDGSTS) pipeline, 16-byte copies for stored operands and 8-byte
 // gathers straight from the L2-resident table for the generated operand.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gemm {
 
-constexpr int BM = 128, BN = 128, BK = 16, THREADS = 256, STAGES = 3;
-constexpr int LDA_S = BK + 4;    // 20 doubles: conflict-free 8-byte fragment loads
-constexpr int LDBN_S = BN + 4;   // 132 doubles
-constexpr int A_STAGE = BM * LDA_S;                // doubles
-constexpr int B_STAGE = (BN * LDA_S > BK * LDBN_S) ? BN * LDA_S : BK * LDBN_S;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+constexpr int BM = 128, BN = 128, THREADS = 256;
+constexpr int LDBN_S = BN + 4;   // 132 doubles: conflict-free 8-byte fragment loads in the N-contiguous layouts
+
+template <int BK>
+struct Cfg {
+    static constexpr int LDA_S = BK + 4;   // (BK + 4) % 16 == 4: conflict-free 8-byte fragment loads
+    static constexpr int A_STAGE = BM * LDA_S;
+    static constexpr int B_STAGE = (BN * LDA_S > BK * LDBN_S) ? BN * LDA_S : BK * LDBN_S;
+    static constexpr int smem_bytes(int stages) { return stages * (A_STAGE + B_STAGE) * (int)sizeof(double); }
+};
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -39,8 +45,16 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-template <int MODE>
+// LATE = 1: the loads of the slab that enters the ring are issued after the first k4 step of the
+// current slab, so the tensor pipe restarts right after the barrier.
+template <int MODE, int BK, int STAGES, int LATE>
 __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const __grid_constant__ TaskBatch batch) {
+    using C = Cfg<BK>;
+    constexpr int LDA_S = C::LDA_S, A_STAGE = C::A_STAGE, B_STAGE = C::B_STAGE;
+    constexpr int CH = BK / 2;                      // 16-byte chunks per operand row
+    constexpr int NA = BM * CH / THREADS;           // A chunks per thread (4 for BK=16, 8 for BK=32)
+    constexpr int NBN = BK * (BN / 2) / THREADS;    // B_N chunks per thread
+    constexpr int NG = BK * BN / THREADS;           // B_GEN elements per thread
     const Task& T = batch.t[blockIdx.z];
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     if (m0 >= T.M || n0 >= T.N) return;
@@ -54,49 +68,47 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const __grid_const
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const int wm = warp >> 2, wn = warp & 3;
-
     const int nk = T.K / BK;
 
     // ---- per-thread copy coordinates
-    // A (and B_T): 1024 16-byte chunks, 4 per thread: row = c / 8, kc = c % 8
-    const double* a_src[4];
-    int a_dst[4];
+    const double* a_src[NA];
+    int a_dst[NA];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        int c = tid + THREADS * q;
-        int row = c >> 3, kc = c & 7;
-        int gr = min(m0 + row, T.M - 1);
+    for (int q = 0; q < NA; ++q) {
+        const int c = tid + THREADS * q;
+        const int row = c / CH, kc = c % CH;
+        const int gr = min(m0 + row, T.M - 1);
         a_src[q] = T.A + (long)gr * T.lda + kc * 2;
         a_dst[q] = row * LDA_S + kc * 2;
     }
-    const double* b_src[4];
-    int b_dst[4];
-    int li = 0;           // B_GEN: lattice id of this thread's output column
-    int lj_next[8];       // B_GEN: lattice ids of the 8 contraction rows this thread gathers (next slab to issue)
-    const int gen_n = tid & (BN - 1), gen_j = tid >> 7;   // 2 j-rows per pass, 8 passes
+    constexpr int NB = (MODE == B_T) ? NA : (MODE == B_N ? NBN : 1);
+    const double* b_src[NB];
+    int b_dst[NB];
+    int li = 0;                 // B_GEN: lattice id of this thread's output column
+    int lj_next[NG];            // B_GEN: lattice ids of the contraction rows this thread gathers (next slab to issue)
+    const int gen_n = tid & (BN - 1), gen_j = tid >> 7;   // 2 j-rows per pass
     if (MODE == B_T) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int c = tid + THREADS * q;
-            int row = c >> 3, kc = c & 7;
-            int gr = min(n0 + row, T.N - 1);
+        for (int q = 0; q < NB; ++q) {
+            const int c = tid + THREADS * q;
+            const int row = c / CH, kc = c % CH;
+            const int gr = min(n0 + row, T.N - 1);
             b_src[q] = T.B + (long)gr * T.ldb + kc * 2;
             b_dst[q] = row * LDA_S + kc * 2;
         }
     } else if (MODE == B_N) {
-        // tile [16][128]: 1024 chunks: krow = c / 64, nc = c % 64
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int c = tid + THREADS * q;
-            int krow = c >> 6, nc = c & 63;
-            long gn = min((long)n0 + nc * 2, T.ldb - 2);
+        for (int q = 0; q < NB; ++q) {
+            const int c = tid + THREADS * q;
+            const int krow = c / (BN / 2), nc = c % (BN / 2);
+            const long gn = min((long)n0 + nc * 2, T.ldb - 2);
             b_src[q] = T.B + (long)krow * T.ldb + gn;
             b_dst[q] = krow * LDBN_S + nc * 2;
         }
     } else {
         li = T.Lrow[min(n0 + gen_n, T.N - 1)];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) lj_next[q] = T.Lcol[min(gen_j + 2 * q, T.K - 1)];
+        for (int q = 0; q < NG; ++q) lj_next[q] = T.Lcol[min(gen_j + 2 * q, T.K - 1)];
     }
 
     auto issue = [&](int kt, int stage) {
@@ -104,21 +116,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const __grid_const
         double* bs = Bs + stage * B_STAGE;
         const long koff = (long)kt * BK;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cp_async16(as + a_dst[q], a_src[q] + koff);
+        for (int q = 0; q < NA; ++q) cp_async16(as + a_dst[q], a_src[q] + koff);
         if (MODE == B_T) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cp_async16(bs + b_dst[q], b_src[q] + koff);
+            for (int q = 0; q < NB; ++q) cp_async16(bs + b_dst[q], b_src[q] + koff);
         } else if (MODE == B_N) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cp_async16(bs + b_dst[q], b_src[q] + koff * T.ldb);
+            for (int q = 0; q < NB; ++q) cp_async16(bs + b_dst[q], b_src[q] + koff * T.ldb);
         } else {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                cp_async8(bs + (gen_j + 2 * q) * LDBN_S + gen_n, T.B + (li - lj_next[q]));
-            // prefetch lattice ids of the slab issued next
-            const int kn = (kt + 1) * BK;
+            for (int q = 0; q < NG; ++q) cp_async8(bs + (gen_j + 2 * q) * LDBN_S + gen_n, T.B + (li - lj_next[q]));
+            const int kn = (kt + 1) * BK;   // prefetch the lattice ids of the slab issued next
 #pragma unroll
-            for (int q = 0; q < 8; ++q) lj_next[q] = T.Lcol[min(kn + gen_j + 2 * q, T.K - 1)];
+            for (int q = 0; q < NG; ++q) lj_next[q] = T.Lcol[min(kn + gen_j + 2 * q, T.K - 1)];
         }
     };
 
@@ -128,7 +138,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const __grid_const
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // ---- prologue
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) issue(s, s);
@@ -138,8 +147,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const __grid_const
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            int kn = kt + STAGES - 1;
+        const int kn = kt + STAGES - 1;
+        if (!LATE) {
             if (kn < nk) issue(kn, kn % STAGES);
             cp_async_commit();
         }
@@ -161,6 +170,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const __grid_const
             for (int mf = 0; mf < 8; ++mf)
 #pragma unroll
                 for (int nf = 0; nf < 4; ++nf) dmma(acc[mf][nf][0], acc[mf][nf][1], a[mf], b[nf]);
+            if (LATE && k4 == 0) {
+                if (kn < nk) issue(kn, kn % STAGES);
+                cp_async_commit();
+            }
         }
     }
     cp_async_wait<0>();
@@ -198,31 +211,52 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const __grid_const
     }
 }
 
+// ---- variant table (GEOBO_B200_GEMM="BK,STAGES,LATE" selects one at context creation; default below)
+typedef void (*kernel_fn)(const TaskBatch);
+struct Variant {
+    int bk, stages, late, smem;
+    kernel_fn fn[3];
+};
+#define GB_VARIANT(BK, ST, LT)                                                                               \
+    {BK, ST, LT, Cfg<BK>::smem_bytes(ST),                                                                    \
+     {gemm_f64_kernel<B_T, BK, ST, LT>, gemm_f64_kernel<B_N, BK, ST, LT>, gemm_f64_kernel<B_GEN, BK, ST, LT>}}
+static const Variant kVariants[] = {
+    GB_VARIANT(16, 3, 0), GB_VARIANT(16, 4, 0), GB_VARIANT(16, 3, 1), GB_VARIANT(16, 4, 1),
+    GB_VARIANT(32, 3, 0), GB_VARIANT(32, 3, 1), GB_VARIANT(32, 2, 0),
+};
+static int g_variant = 5;   // BK = 32, 3 stages, late issue: fastest in the round-1 sweep (profiles/README.md)
+
 cudaError_t init() {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(gemm_f64_kernel<B_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_f64_kernel<B_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_f64_kernel<B_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    return e;
+    const char* env = getenv("GEOBO_B200_GEMM");
+    if (env) {
+        int bk = 0, st = 0, lt = 0;
+        if (sscanf(env, "%d,%d,%d", &bk, &st, &lt) == 3) {
+            for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
+                if (kVariants[i].bk == bk && kVariants[i].stages == st && kVariants[i].late == lt) g_variant = (int)i;
+        }
+    }
+    const Variant& v = kVariants[g_variant];
+    for (int m = 0; m < 3; ++m) {
+        cudaError_t e = cudaFuncSetAttribute(v.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
+int tile_k() { return kVariants[g_variant].bk; }
+
 cudaError_t launch(const TaskBatch& batch, BMode mode, cudaStream_t stream) {
+    const Variant& v = kVariants[g_variant];
     int maxM = 0, maxN = 0;
     for (int i = 0; i < batch.n; ++i) {
-        if (batch.t[i].K % BK != 0) return cudaErrorInvalidValue;
+        if (batch.t[i].K % v.bk != 0) return cudaErrorInvalidValue;
         maxM = max(maxM, batch.t[i].M);
         maxN = max(maxN, batch.t[i].N);
     }
     if (batch.n == 0 || maxM == 0 || maxN == 0) return cudaSuccess;
     dim3 grid((maxN + BN - 1) / BN, (maxM + BM - 1) / BM, batch.n);
     if (grid.y > 65535) return cudaErrorInvalidValue;
-    switch (mode) {
-        case B_T: gemm_f64_kernel<B_T><<<grid, THREADS, SMEM_BYTES, stream>>>(batch); break;
-        case B_N: gemm_f64_kernel<B_N><<<grid, THREADS, SMEM_BYTES, stream>>>(batch); break;
-        case B_GEN: gemm_f64_kernel<B_GEN><<<grid, THREADS, SMEM_BYTES, stream>>>(batch); break;
-    }
+    v.fn[(int)mode]<<<grid, THREADS, v.smem, stream>>>(batch);
     return cudaGetLastError();
 }
 
