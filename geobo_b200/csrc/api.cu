@@ -247,6 +247,11 @@ struct gb_problem {
     int* info = nullptr;
     double* mu = nullptr;                // [3][ncol]
     double* var = nullptr;               // [3][ncol]
+    uint8_t* a8[2] = {nullptr, nullptr};   // int8 digit planes of the sensitivities (tcgen05 path, built lazily)
+    int* a_exp[2] = {nullptr, nullptr};
+    uint8_t* t8 = nullptr;
+    int* t_exp = nullptr;
+    int a8_slices = 0;
     double* y_host_pinned = nullptr;
     double* out_pinned = nullptr;        // [6*ncol + 4]
     cudaEvent_t ev[GB_NUM_TIMERS + 1];
@@ -271,6 +276,7 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
+                    p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp,
                     p->linv, p->scal, p->info, p->mu, p->var};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -498,7 +504,33 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     GB_CUDA(ctx, cudaEventRecord(p->ev[1], s));
 
     // ---- Pt = A3 . K : fused assembly + projection, 6 (data block c, property block r) products
-    {
+    if (h->slices != 0) {
+        // int8 digit-slice products on tcgen05 / TMEM (ozaki.cu); everything downstream stays fp64
+        const int S = h->slices;
+        if (ozaki_tile_n(S) == 0) return gb_fail(ctx, GB_ERR_ARG, "gb_hyper.slices must be 0 (fp64) or 4, 5, 6; got %d", S);
+        if (p->n[2] % 16 != 0)
+            return gb_fail(ctx, GB_ERR_UNSUPPORTED, "the int8 tensor-core path needs zNcube %% 16 == 0 (got %lld); use slices = 0",
+                           (long long)p->n[2]);
+        if (p->a8_slices != S) {   // digit planes of the sensitivities: built once per problem and slice count
+            for (int c = 0; c < 2; ++c) {
+                if (p->a8[c]) { cudaFree(p->a8[c]); p->a8[c] = nullptr; }
+                GB_CUDA(ctx, cudaMalloc((void**)&p->a8[c], (size_t)S * Ns * p->Kp));
+                if (!p->a_exp[c]) GB_CUDA(ctx, cudaMalloc((void**)&p->a_exp[c], (size_t)Ns * sizeof(int)));
+                GB_CUDA(ctx, ozaki_slice_sens(p->A[c], Ns, p->N, p->lda, S, p->a_exp[c], p->a8[c], p->Kp, s));
+            }
+            if (p->t8) { cudaFree(p->t8); p->t8 = nullptr; }
+            GB_CUDA(ctx, cudaMalloc((void**)&p->t8, (size_t)ozaki_table_bytes(p->ext, S)));
+            if (!p->t_exp) GB_CUDA(ctx, cudaMalloc((void**)&p->t_exp, 16 * sizeof(int)));
+            p->a8_slices = S;
+        }
+        GB_CUDA(ctx, ozaki_slice_tables(p->tables, p->ext, S, p->t_exp, p->t8, s));
+        OzakiArgs oa;
+        oa.a8[0] = p->a8[0]; oa.a8[1] = p->a8[1]; oa.a_exp[0] = p->a_exp[0]; oa.a_exp[1] = p->a_exp[1];
+        oa.t8 = p->t8; oa.t_exp = p->t_exp; oa.L = p->L; oa.Pt = p->Pt;
+        oa.ext = p->ext; oa.C0 = p->C0; oa.kp = p->Kp; oa.ldp = ldp; oa.ncp = ncp;
+        oa.Ns = (int)Ns; oa.ncol = (int)ncol; oa.c0 = (int)p->c0;
+        GB_CUDA(ctx, ozaki_project(oa, S, ctx->sm_count, s));
+    } else {
         gemm::TaskBatch b;
         b.n = 0;
         for (int c = 0; c < 2; ++c)

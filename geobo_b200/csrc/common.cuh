@@ -117,6 +117,24 @@ cudaError_t launch_a_drill(const double* loc, int64_t nd, const double* vp, int6
 cudaError_t launch_gemv(const double* A, int64_t rows, int64_t cols, int64_t ld, const double* x, double* y,
                         cudaStream_t s);
 
+// int8 digit-slice projection on tcgen05 (ozaki.cu)
+struct OzakiArgs {
+    const uint8_t* a8[2];    // digit planes of A_grav / A_magn: [slice][Ns][kp]
+    const int* a_exp[2];     // per-sensor-row exponents
+    const uint8_t* t8;       // digit planes of the 9 covariance tables
+    const int* t_exp;        // per-table exponents
+    const int* L;            // extended-lattice ids [kp]
+    double* Pt;
+    long ext, C0, kp, ldp, ncp;
+    int Ns, ncol, c0;
+};
+int ozaki_tile_n(int slices);
+long ozaki_table_bytes(long ext, int slices);
+cudaError_t ozaki_slice_sens(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp,
+                             cudaStream_t s);
+cudaError_t ozaki_slice_tables(const double* tables, long ext, int slices, int* exps, uint8_t* out, cudaStream_t s);
+cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStream_t s);
+
 // Cholesky / triangular solve (chol.cu)
 struct CholWork {
     double* linv = nullptr;   // [Mp/128][128][128] inverses of the diagonal blocks

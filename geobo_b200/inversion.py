@@ -71,10 +71,23 @@ class Inversion:
         return self.voxelpos
 
     # ------------------------------------------------------------------ device problem
+    @staticmethod
+    def _slices():
+        """Optional settings key ``precision`` (absent in reference YAMLs -> 'fp64'):
+        'fp64'   : projection A.K on the fp64 tensor pipe (DMMA);
+        'int8x4' / 'int8x5' / 'int8x6' : error-free int8 digit products on tcgen05/TMEM with 31 / 39 / 47 bits per
+        operand (everything after the projection stays fp64).  Needs zNcube % 16 == 0."""
+        prec = str(getattr(_cfg, "precision", "fp64")).lower()
+        if prec in ("fp64", "f64", "double"):
+            return 0
+        if prec in ("int8x4", "int8x5", "int8x6"):
+            return int(prec[-1])
+        raise ValueError("settings key 'precision' must be 'fp64', 'int8x4', 'int8x5' or 'int8x6', got %r" % prec)
+
     def _hyper(self, gp_length=None, coeffm=None, gp_amp=None):
         return _lib.Problem.hyper(self.gp_length if gp_length is None else gp_length, self.gp_sigma,
                                   self.coeffm if coeffm is None else coeffm,
-                                  self.gp_amp if gp_amp is None else gp_amp, _cfg.kernelfunc)
+                                  self.gp_amp if gp_amp is None else gp_amp, _cfg.kernelfunc, self._slices())
 
     def _build_problem(self):
         if not hasattr(self, "Edges"):

@@ -137,7 +137,8 @@ typedef struct gb_hyper {
     double coeffm[3];          /* cross weights w1,w2,w3 (kernels.py:181)                  */
     double gp_amp;             /* amplitude (inversion.py:92)                              */
     int kernel_id;             /* GB_KERNEL_*                                              */
-    int reserved;
+    int slices;                /* 0: fp64 tensor pipe (DMMA) for the projection; 4, 5, 6: error-free int8 digit
+                                  products on tcgen05/TMEM with 7+8(slices-1) bits per operand (needs zNcube % 16 == 0) */
 } gb_hyper;
 
 /* Builds the device-resident problem: computes both sensitivity matrices on the GPU
