@@ -124,8 +124,9 @@ def run_ours(args):
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     xN, yN, zN = wl["shape"]
-    cfg = synth.settings(xN, yN, zN, kernelfunc=wl["kernel"])
+    cfg = synth.settings(xN, yN, zN, kernelfunc=wl["kernel"], precision=args.precision)
     config_loader.load_settings(cfg, make_outpath=False)
+    slices = inversion.Inversion._slices()
     N, Ns, nd = xN * yN * zN, xN * yN, wl["nd"]
     f = synth.make_inputs(nd=nd, seed=0, ctx=ctx)
     info = ctx.device_info()
@@ -143,7 +144,7 @@ def run_ours(args):
     y = np.hstack([(f["grav"] - f["grav"].mean()) / f["grav"].std(), (f["mag"] - f["mag"].mean()) / f["mag"].std(),
                    (f["drillfield"] - f["drillfield"].mean()) / f["drillfield"].std() if nd else np.zeros(0)])
     prob.set_data(y)
-    h = prob.hyper(gl_eff, config_loader.gp_err, config_loader.gp_coeff, 1.0, wl["kernel"])
+    h = prob.hyper(gl_eff, config_loader.gp_err, config_loader.gp_coeff, 1.0, wl["kernel"], slices=slices)
     t_sens_ms = prob.timings()["a_sens"]
     for _ in range(args.warmup):
         prob.predict(h, want_host=False)
@@ -314,6 +315,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GEOBO_B200_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("GEOBO_B200_PRECISION", "fp64"),
+                    choices=["fp64", "int8x4", "int8x5", "int8x6"],
+                    help="projection arithmetic: fp64 DMMA, or error-free int8 digit products on tcgen05 (31/39/47 bits)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

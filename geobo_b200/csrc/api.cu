@@ -508,13 +508,13 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         // int8 digit-slice products on tcgen05 / TMEM (ozaki.cu); everything downstream stays fp64
         const int S = h->slices;
         if (ozaki_tile_n(S) == 0) return gb_fail(ctx, GB_ERR_ARG, "gb_hyper.slices must be 0 (fp64) or 4, 5, 6; got %d", S);
-        if (p->n[2] % 16 != 0)
-            return gb_fail(ctx, GB_ERR_UNSUPPORTED, "the int8 tensor-core path needs zNcube %% 16 == 0 (got %lld); use slices = 0",
-                           (long long)p->n[2]);
+        if (p->n[2] % 16 != 0 || ncol % 16 != 0)
+            return gb_fail(ctx, GB_ERR_UNSUPPORTED, "the int8 tensor-core path needs zNcube %% 16 == 0 and a voxel-column shard that is a multiple of 16 "
+                           "(got zNcube=%lld, columns=%ld); use slices = 0", (long long)p->n[2], ncol);
         if (p->a8_slices != S) {   // digit planes of the sensitivities: built once per problem and slice count
             for (int c = 0; c < 2; ++c) {
                 if (p->a8[c]) { cudaFree(p->a8[c]); p->a8[c] = nullptr; }
-                GB_CUDA(ctx, cudaMalloc((void**)&p->a8[c], (size_t)S * Ns * p->Kp));
+                GB_CUDA(ctx, cudaMalloc((void**)&p->a8[c], (size_t)ozaki_rows_bytes(Ns, p->Kp, S)));
                 if (!p->a_exp[c]) GB_CUDA(ctx, cudaMalloc((void**)&p->a_exp[c], (size_t)Ns * sizeof(int)));
                 GB_CUDA(ctx, ozaki_slice_sens(p->A[c], Ns, p->N, p->lda, S, p->a_exp[c], p->a8[c], p->Kp, s));
             }

@@ -119,7 +119,7 @@ cudaError_t launch_gemv(const double* A, int64_t rows, int64_t cols, int64_t ld,
 
 // int8 digit-slice projection on tcgen05 (ozaki.cu)
 struct OzakiArgs {
-    const uint8_t* a8[2];    // digit planes of A_grav / A_magn: [slice][Ns][kp]
+    const uint8_t* a8[2];    // pre-tiled digit blocks of A_grav / A_magn: [row tile][k step][slice][4096 B]
     const int* a_exp[2];     // per-sensor-row exponents
     const uint8_t* t8;       // digit planes of the 9 covariance tables
     const int* t_exp;        // per-table exponents
@@ -130,6 +130,7 @@ struct OzakiArgs {
 };
 int ozaki_tile_n(int slices);
 long ozaki_table_bytes(long ext, int slices);
+long ozaki_rows_bytes(long rows, long kp, int slices);
 cudaError_t ozaki_slice_sens(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp,
                              cudaStream_t s);
 cudaError_t ozaki_slice_tables(const double* tables, long ext, int slices, int* exps, uint8_t* out, cudaStream_t s);

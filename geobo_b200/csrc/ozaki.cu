@@ -3,19 +3,27 @@
 //
 // tcgen05 has no fp64 kind and the path is too ill-conditioned for tf32/bf16, so the
 // fp64 operands are split into S fixed-point digits of 7 / 8 bits:
-//     x = 2^e * sum_q d_q 2^-(7+8q),   d_0 in [-64, 64] (signed), d_q>0 in [0, 255] (unsigned),
+//     x = 2^e * sum_q d_q 2^-(7+8q),   balanced digits d_q in [-128, 127] (all signed),
 // with one exponent per sensor row of A and one per covariance table.  Digit products are accumulated EXACTLY
 // in int32 by `tcgen05.mma.kind::i8` (SASS UTCIMMA), one TMEM accumulator per significance level
-// l = qa + qb <= S-1 (S(S+1)/2 MMAs per K = 32 step), flushed every CHUNK contraction indices (overflow bound)
+// l = qa + qb <= S-1 (S(S+1)/2 digit products per K = 32 step, issued as wide-N instructions that multiply one A digit
+// with up to 256 / NT consecutive B digits at once), flushed every CHUNK contraction indices (overflow bound)
 // into the fp64 result with an exact int64 recombination.  The only error is the truncation of the operands
 // to 7 + 8(S-1) bits (S = 5: 2^-39 relative to the row / table scale) and of levels >= S.
 //
-// CTA = 13 warps, persistent (one CTA per SM): warps 0-3 epilogue (TMEM -> int64 -> fp64 read-modify-write of
-// the Pt tile), warp 4 TMEM allocator + single-thread MMA issuer, warps 5-12 producers: the A digits stream in
-// with 16-byte cp.async, the K digits are GENERATED: for 16 consecutive contraction voxels in one z-column the
-// 16 digit bytes are one unaligned window of the (symmetric) stationary-covariance byte table, fetched with five
-// aligned 32-bit loads + funnel shifts and stored straight into the UMMA canonical (K-major, no-swizzle) layout.
-// Stage hand-off is mbarrier based (full: producers -> MMA, empty: tcgen05.commit -> producers).
+// CTA = 5 + W warps, persistent (one CTA per SM): warps 0-3 epilogue (TMEM -> int64 -> fp64 read-modify-write of
+// the Pt tile), warp 4 TMEM allocator + single-thread MMA issuer, warps 5.. producers; producer warp w owns the
+// pipeline stages st = w (mod W) (STAGES is a multiple of W, so one warp sees every use of its stages in order
+// and mbarrier parities stay unambiguous) and fills a whole K = 32 stage on its own, so W stages are in flight:
+//   * A digits: stored in global memory PRE-TILED in the UMMA canonical (K-major, no-swizzle) layout
+//     [row tile][k step][digit][4096 B], so one stage of A is one contiguous S * 4096-byte block fetched with a
+//     single bulk async copy (cp.async.bulk -> SASS UBLKCP) that signals the stage's mbarrier (complete_tx);
+//   * K digits are GENERATED: for 16 consecutive output voxels i and 16 consecutive contraction voxels j (both in
+//     one z-column, z fastest) the 16 x 16 digit block is Toeplitz in the stationary-covariance byte table --
+//     47 table bytes.  A half-warp loads the aligned words of that stretch once (one 32-bit load per lane), every
+//     lane picks its own unaligned 16-byte window with five shuffles + funnel shifts and stores it straight into
+//     the canonical layout (one conflict-free 16-byte st.shared per lane, digit and 16-column segment).
+// Stage hand-off is mbarrier based (full: producer warp + bulk-copy bytes -> MMA, empty: tcgen05.commit -> producer).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -23,28 +31,40 @@ using namespace umma;
 
 namespace ozaki {
 
-constexpr int NPROD_WARPS = 8, NPROD = NPROD_WARPS * 32;
-constexpr int THREADS = (4 + 1 + NPROD_WARPS) * 32;   // 416
-constexpr int STAGES = 4;
 constexpr int TABLE_PAD = 64;
 __host__ __device__ constexpr long plane_stride(long ext) { return (ext + TABLE_PAD + 15) & ~15L; }   // keeps every digit plane 16-byte aligned
 
+// Tile shape per slice count: the S accumulators of one 128 x NT tile fill TMEM (S * NT <= 512 columns);
+// W producer warps, STAGES (multiple of W) shared-memory stages of S * (4096 + NT * 32) bytes.
+template <int S> struct Cfg;
+template <> struct Cfg<4> { static constexpr int NT = 128, W = 6, STAGES = 6; };
+template <> struct Cfg<5> { static constexpr int NT = 96, W = 6, STAGES = 6; };
+template <> struct Cfg<6> { static constexpr int NT = 80, W = 5, STAGES = 5; };
+
 // ------------------------------------------------------------------------------------------------ digit extraction
-// t in (-1/2, 1/2): digits of t + half an ulp of the last digit (round to nearest overall)
+// t in [-1/2, 1/2]: BALANCED digits (every d_q in [-128, 127], stored as two's-complement bytes) of t rounded to
+// nearest at the last digit:  t ~ sum_q d_q 2^-(7 + 8 q).  All digits signed => one instruction descriptor for every
+// digit pair, several B digits can share one wide-N MMA, and the worst-case accumulator growth is 4x smaller.
 template <int S>
 __device__ __forceinline__ void digits(double t, uint8_t (&d)[S]) {
     t += ldexp(1.0, -(7 + 8 * (S - 1) + 1));
+    int v[S];
     double x = t * 128.0;
     double f = floor(x);
-    d[0] = (uint8_t)(int8_t)(int)f;
+    v[0] = (int)f;                       // in [-64, 64]
     double r = x - f;
 #pragma unroll
     for (int q = 1; q < S; ++q) {
         x = r * 256.0;
         f = floor(x);
-        d[q] = (uint8_t)(int)f;
+        v[q] = (int)f;                   // in [0, 255]
         r = x - f;
     }
+#pragma unroll
+    for (int q = S - 1; q >= 1; --q)
+        if (v[q] >= 128) { v[q] -= 256; v[q - 1] += 1; }
+#pragma unroll
+    for (int q = 0; q < S; ++q) d[q] = (uint8_t)(int8_t)v[q];
 }
 
 // exponent e with |x| <= 2^(e-1)  (so t = x / 2^e lies in [-1/2, 1/2])
@@ -66,22 +86,35 @@ __global__ void row_absmax_kernel(const double* __restrict__ A, long rows, long 
     if (lane == 0) exps[row] = scale_exp(m);
 }
 
-// A (rows x ld fp64, cols valid) -> S digit planes [q][rows][kp] (bytes; columns >= cols are zero)
+// A (rows x ld fp64, cols valid) -> pre-tiled digit blocks [row tile][k step][digit][4096 B canonical layout];
+// one thread per (row, 16 consecutive contraction indices): S 16-byte stores.  Rows >= rows and columns >= cols are zero.
 template <int S>
-__global__ void slice_rows_kernel(const double* __restrict__ A, long rows, long cols, long ld, const int* __restrict__ exps,
-                                  uint8_t* __restrict__ out, long kp) {
-    const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void slice_rows_tiled_kernel(const double* __restrict__ A, long rows, long cols, long ld, const int* __restrict__ exps,
+                                        uint8_t* __restrict__ out, long ksteps) {
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;    // 16-column group
     const long row = blockIdx.y;
-    if (col >= kp) return;
-    uint8_t d[S];
-    if (col < cols) {
-        digits<S>(ldexp(A[row * ld + col], -exps[row]), d);
-    } else {
+    if (g >= 2 * ksteps) return;
+    uint32_t pk[S][4];
 #pragma unroll
-        for (int q = 0; q < S; ++q) d[q] = 0;
+    for (int q = 0; q < S; ++q) pk[q][0] = pk[q][1] = pk[q][2] = pk[q][3] = 0u;
+    if (row < rows) {
+        const int e = exps[row];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const long col = g * 16 + b;
+            if (col < cols) {
+                uint8_t d[S];
+                digits<S>(ldexp(A[row * ld + col], -e), d);
+#pragma unroll
+                for (int q = 0; q < S; ++q) pk[q][b >> 2] |= (uint32_t)d[q] << (8 * (b & 3));
+            }
+        }
     }
+    const long stile = row >> 7, ks = g >> 1;
+    const uint32_t off = core_offset((uint32_t)(row & 127), (uint32_t)(g & 1));
 #pragma unroll
-    for (int q = 0; q < S; ++q) out[((long)q * rows + row) * kp + col] = d[q];
+    for (int q = 0; q < S; ++q)
+        *reinterpret_cast<uint4*>(out + ((stile * ksteps + ks) * S + q) * 4096 + off) = make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
 }
 
 __global__ void table_absmax_kernel(const double* __restrict__ tab, long ext, int* __restrict__ exps) {
@@ -117,7 +150,7 @@ __global__ void slice_table_kernel(const double* __restrict__ tab, long ext, con
 
 // ------------------------------------------------------------------------------------------------ main kernel
 struct Params {
-    const uint8_t* a8[2];     // [q][Ns][kp] digit planes of A_grav / A_magn
+    const uint8_t* a8[2];     // pre-tiled digit blocks of A_grav / A_magn: [row tile][k step][digit][4096]
     const int* a_exp[2];      // [Ns]
     const uint8_t* t8;        // [9][S][plane_stride(ext)] digit planes of the covariance tables (only c = 0, 1 are used)
     const int* t_exp;         // [9]
@@ -128,11 +161,14 @@ struct Params {
     int n_stile, n_itile;
 };
 
-template <int S, int NT>
-__global__ void __launch_bounds__(THREADS, 1) ozaki_project_kernel(const __grid_constant__ Params P) {
+template <int S>
+__global__ void __launch_bounds__((5 + Cfg<S>::W) * 32, 1) ozaki_project_kernel(const __grid_constant__ Params P) {
+    constexpr int NT = Cfg<S>::NT, W = Cfg<S>::W, STAGES = Cfg<S>::STAGES, NSEG = NT / 16;
     constexpr int A_BYTES = S * 4096, B_SLICE = NT * 32, STAGE_BYTES = A_BYTES + S * B_SLICE;
     constexpr int TMEM_COLS = 512;
+    constexpr int G = 256 / NT;          // B digits per MMA instruction (N <= 256)
     static_assert(S * NT <= TMEM_COLS, "accumulators do not fit in TMEM");
+    static_assert(STAGES % W == 0, "a producer warp must own its stages");
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar, tempty_bar;
     __shared__ uint32_t tmem_base_s;
@@ -141,7 +177,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_project_kernel(const __grid_
     if (warp == 4) {
         tmem_alloc(&tmem_base_s, TMEM_COLS);
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NPROD); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
             mbar_init(&tfull_bar, 1);
             mbar_init(&tempty_bar, 128);
             fence_barrier_init();
@@ -154,99 +190,107 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_project_kernel(const __grid_
 
     const long tiles_per_task = (long)P.n_stile * P.n_itile;
     const long ntiles = 6 * tiles_per_task;
-    const int nchunk = (int)((P.kp + P.chunk - 1) / P.chunk);
+    const int ksteps = (int)(P.kp / 32);
+    const int chunk_steps = P.chunk / 32;
 
     if (warp >= 5) {
-        // =============================================================== producers
-        const int pt = tid - 5 * 32;                 // 0 .. 255
-        const bool gen = pt < 2 * NT;                // one (column n, k-half) unit per thread
-        const int gn = pt >> 1, gkh = pt & 1;
-        uint32_t it = 0;
-        int prev_stage = -1;
-        for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // =============================================================== producers (one warp per stage)
+        const int w = warp - 5;
+        const int n = lane & 15, kh = lane >> 4;      // lane <-> (column within a 16-column segment, 16-byte K half)
+        const long plane = plane_stride(P.ext);
+        const int C0 = (int)P.C0;
+        uint32_t it_tile0 = 0;
+        for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it_tile0 += (uint32_t)ksteps) {
             const int task = (int)(tile / tiles_per_task);            // c * 3 + r
             const long rem = tile % tiles_per_task;
             const int stile = (int)(rem / P.n_itile), itile = (int)(rem % P.n_itile);
             const int c = task / 3;
-            const int s0 = stile * 128, i0 = itile * NT;
-            const uint8_t* a8 = P.a8[c];
-            const uint8_t* t8 = P.t8 + (long)task * S * plane_stride(P.ext);
-            long li = 0;
-            if (gen) li = (long)P.L[P.c0 + min(i0 + gn, P.ncol - 1)];
-            for (int ch = 0; ch < nchunk; ++ch) {
-                const long jbeg = (long)ch * P.chunk, jend = min(P.kp, jbeg + P.chunk);
-                for (long j0 = jbeg; j0 < jend; j0 += 32, ++it) {
-                    const int st = it % STAGES;
-                    mbar_wait(&empty_bar[st], ((it / STAGES) & 1) ^ 1);
-                    uint8_t* sa = smem + st * STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
-                    // ---- A digits: S x 128 rows x 2 halves of 16 bytes, cp.async
-                    for (int e = pt; e < S * 256; e += NPROD) {
-                        const int q = e >> 8, r2 = e & 255, row = r2 >> 1, kh = r2 & 1;
-                        const int gr = min(s0 + row, P.Ns - 1);
-                        const uint8_t* src = a8 + ((long)q * P.Ns + gr) * P.kp + j0 + kh * 16;
-                        const uint32_t dst = smem_u32(sa + q * 4096 + core_offset(row, kh));
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
-                    }
-                    asm volatile("cp.async.commit_group;");
-                    // ---- K digits: one unaligned 16-byte window of the byte table per (column, half, digit)
-                    if (gen) {
-                        const long off = P.C0 + (long)P.L[j0 + gkh * 16] - li;      // symmetric table: index L(j) - L(i) + C0
-                        const uint32_t sh = (uint32_t)(off & 3) * 8;
-                        const uint8_t* base = t8 + (off & ~3L);
-#pragma unroll
-                        for (int q = 0; q < S; ++q) {
-                            const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (long)q * plane_stride(P.ext));
-                            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
-                            uint4 v;
-                            v.x = __funnelshift_r(w0, w1, sh);
-                            v.y = __funnelshift_r(w1, w2, sh);
-                            v.z = __funnelshift_r(w2, w3, sh);
-                            v.w = __funnelshift_r(w3, w4, sh);
-                            *reinterpret_cast<uint4*>(sb + q * B_SLICE + core_offset(gn, gkh)) = v;
-                        }
-                    }
-                    // ---- publish the PREVIOUS stage (its cp.async group has had a whole step to land)
-                    if (prev_stage >= 0) {
-                        asm volatile("cp.async.wait_group 1;" ::: "memory");
-                        fence_proxy_async_smem();
-                        mbar_arrive(&full_bar[prev_stage]);
-                    }
-                    prev_stage = st;
+            const int i0 = itile * NT;
+            const uint8_t* a_src = P.a8[c] + (size_t)stile * ksteps * A_BYTES;
+            const uint8_t* t8 = P.t8 + (size_t)task * S * plane;
+            int li_reg = 0;                                // lattice id of the first column of segment `lane`
+            if (lane < NSEG) li_reg = P.L[P.c0 + min(i0 + lane * 16, P.ncol - 16)];
+            int ks = (int)((uint32_t)(w + W - (int)(it_tile0 % W)) % W);
+            int lj_next = ks < ksteps ? P.L[ks * 32 + kh * 16] : 0;
+            for (; ks < ksteps; ks += W) {
+                const uint32_t it = it_tile0 + (uint32_t)ks;
+                const int st = (int)(it % STAGES);
+                const int lj = lj_next;
+                if (ks + W < ksteps) lj_next = P.L[(ks + W) * 32 + kh * 16];
+                mbar_wait(&empty_bar[st], ((it / STAGES) & 1) ^ 1);
+                uint8_t* sa = smem + st * STAGE_BYTES;
+                uint8_t* sb = sa + A_BYTES;
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full_bar[st], A_BYTES);
+                    bulk_g2s(sa, a_src + (size_t)ks * A_BYTES, A_BYTES, &full_bar[st]);
                 }
+                // ---- K digits, phase 1: every half-warp loads the aligned words covering its 31-byte table stretch
+                uint32_t word[NSEG][S];
+                int wi[NSEG];
+                uint32_t sh[NSEG];
+#pragma unroll
+                for (int sg = 0; sg < NSEG; ++sg) {
+                    const int li = __shfl_sync(0xffffffffu, li_reg, sg);
+                    const int offmin = C0 + lj - li - 15;          // table offset of (i = segment start + 15, j = half start); symmetric table
+                    const int d = (offmin & 3) + 15 - n;           // this lane's window starts d bytes after the aligned base
+                    wi[sg] = d >> 2;
+                    sh[sg] = (uint32_t)(d & 3) * 8;
+                    const uint8_t* src = t8 + (offmin & ~3) + 4 * n;
+#pragma unroll
+                    for (int q = 0; q < S; ++q) word[sg][q] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)q * plane));
+                }
+                // ---- phase 2: pick the unaligned 16-byte window (5 words) and store it in canonical layout
+#pragma unroll
+                for (int sg = 0; sg < NSEG; ++sg) {
+                    const int src_lane = (lane & 16) + wi[sg];
+#pragma unroll
+                    for (int q = 0; q < S; ++q) {
+                        const uint32_t w0 = __shfl_sync(0xffffffffu, word[sg][q], src_lane);
+                        const uint32_t w1 = __shfl_sync(0xffffffffu, word[sg][q], src_lane + 1);
+                        const uint32_t w2 = __shfl_sync(0xffffffffu, word[sg][q], src_lane + 2);
+                        const uint32_t w3 = __shfl_sync(0xffffffffu, word[sg][q], src_lane + 3);
+                        const uint32_t w4 = __shfl_sync(0xffffffffu, word[sg][q], src_lane + 4);
+                        uint4 v;
+                        v.x = __funnelshift_r(w0, w1, sh[sg]);
+                        v.y = __funnelshift_r(w1, w2, sh[sg]);
+                        v.z = __funnelshift_r(w2, w3, sh[sg]);
+                        v.w = __funnelshift_r(w3, w4, sh[sg]);
+                        *reinterpret_cast<uint4*>(sb + q * B_SLICE + core_offset(sg * 16 + n, kh)) = v;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[st]);
             }
-        }
-        if (prev_stage >= 0) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            fence_proxy_async_smem();
-            mbar_arrive(&full_bar[prev_stage]);
         }
     } else if (warp == 4) {
         // =============================================================== MMA issuer (one thread)
         if (lane == 0) {
             uint32_t it = 0, chunk_id = 0;
             for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int ch = 0; ch < nchunk; ++ch, ++chunk_id) {
-                    const long jbeg = (long)ch * P.chunk, jend = min(P.kp, jbeg + P.chunk);
+                for (int k0 = 0; k0 < ksteps; k0 += chunk_steps, ++chunk_id) {
+                    const int k1 = min(ksteps, k0 + chunk_steps);
                     mbar_wait(&tempty_bar, (chunk_id & 1) ^ 1);     // epilogue has drained the accumulators
                     tc_fence_after();
-                    bool first = true;
-                    for (long j0 = jbeg; j0 < jend; j0 += 32, ++it) {
-                        const int st = it % STAGES;
+                    for (int ks = k0; ks < k1; ++ks, ++it) {
+                        const int st = (int)(it % STAGES);
                         mbar_wait(&full_bar[st], (it / STAGES) & 1);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(smem + st * STAGE_BYTES), sb = sa + A_BYTES;
+                        const uint32_t acc = ks == k0 ? 0u : 1u;
+                        // A digit qa times B digits qb0 .. qb0+g-1 in ONE instruction of N = g * NT columns: the B digit
+                        // planes are consecutive rows of the canonical layout and product (qa, qb) lands in the
+                        // accumulator of level qa + qb at column (qa + qb) * NT.
 #pragma unroll
-                        for (int lvl = 0; lvl < S; ++lvl) {
+                        for (int qa = 0; qa < S; ++qa) {
+                            const uint64_t ad = smem_desc(sa + qa * 4096, kLBO, kSBO);
 #pragma unroll
-                            for (int qa = 0; qa <= lvl; ++qa) {
-                                const int qb = lvl - qa;
-                                const uint64_t ad = smem_desc(sa + qa * 4096, kLBO, kSBO);
-                                const uint64_t bd = smem_desc(sb + qb * B_SLICE, kLBO, kSBO);
-                                mma_i8(tmem_base + lvl * NT, ad, bd, idesc_i8(qa == 0, qb == 0, NT), (first && qa == 0) ? 0u : 1u);
+                            for (int qb0 = 0; qb0 < S - qa; qb0 += G) {
+                                const int g = (S - qa - qb0) < G ? (S - qa - qb0) : G;
+                                const uint64_t bd = smem_desc(sb + qb0 * B_SLICE, kLBO, kSBO);
+                                mma_i8(tmem_base + (qa + qb0) * NT, ad, bd, idesc_i8(1, 1, g * NT), qa == 0 ? acc : 1u);
                             }
                         }
-                        first = false;
                         mma_commit(&empty_bar[st]);       // stage reusable once these MMAs have read it
                     }
                     mma_commit(&tfull_bar);               // accumulators of this chunk complete
@@ -267,7 +311,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_project_kernel(const __grid_
             // result = 2^(eA + eK - 14 - 8 (S-1)) * sum_l acc_l 2^(8 (S-1-l))
             const double scale = row_ok ? ldexp(1.0, P.a_exp[c][s] + P.t_exp[task] - 14 - 8 * (S - 1)) : 0.0;
             double* prow = P.Pt + ((long)c * P.Ns + (row_ok ? s : 0)) * P.ldp + (long)r * P.ncp + i0;
-            for (int ch = 0; ch < nchunk; ++ch, ++chunk_id) {
+            for (int k0 = 0; k0 < ksteps; k0 += chunk_steps, ++chunk_id) {
                 mbar_wait(&tfull_bar, chunk_id & 1);
                 tc_fence_after();
                 for (int n0 = 0; n0 < NT; n0 += 8) {
@@ -284,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_project_kernel(const __grid_
                             const int col = i0 + n0 + k;
                             if (col < P.ncol) {
                                 const double add = scale * (double)acc;
-                                prow[n0 + k] = (ch == 0) ? add : prow[n0 + k] + add;
+                                prow[n0 + k] = (k0 == 0) ? add : prow[n0 + k] + add;
                             }
                         }
                     }
@@ -299,31 +343,36 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_project_kernel(const __grid_
     if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int S, int NT>
+template <int S>
 static cudaError_t launch_one(const Params& P, int sm_count, cudaStream_t s) {
-    constexpr int smem = STAGES * (S * 4096 + S * NT * 32);
-    cudaError_t e = cudaFuncSetAttribute(ozaki_project_kernel<S, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    constexpr int NT = Cfg<S>::NT;
+    constexpr int smem = Cfg<S>::STAGES * (S * 4096 + S * NT * 32);
+    cudaError_t e = cudaFuncSetAttribute(ozaki_project_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     Params q = P;
     q.n_itile = (P.ncol + NT - 1) / NT;
     const long ntiles = 6L * q.n_stile * q.n_itile;
     const int grid = (int)(ntiles < (long)sm_count ? ntiles : (long)sm_count);
-    ozaki_project_kernel<S, NT><<<grid, THREADS, smem, s>>>(q);
+    ozaki_project_kernel<S><<<grid, (5 + Cfg<S>::W) * 32, smem, s>>>(q);
     return cudaGetLastError();
 }
 
 }  // namespace ozaki
 
 // ------------------------------------------------------------------------------------------------ host entry points
-int ozaki_tile_n(int slices) { return slices == 4 ? 128 : slices == 5 ? 96 : slices == 6 ? 80 : 0; }
+int ozaki_tile_n(int slices) { return slices == 4 ? ozaki::Cfg<4>::NT : slices == 5 ? ozaki::Cfg<5>::NT : slices == 6 ? ozaki::Cfg<6>::NT : 0; }
+
+// bytes of the pre-tiled digit blocks of a rows x kp operand
+long ozaki_rows_bytes(long rows, long kp, int slices) { return ((rows + 127) / 128) * (kp / 32) * (long)slices * 4096; }
 
 cudaError_t ozaki_slice_sens(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp, cudaStream_t s) {
     ozaki::row_absmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(A, rows, cols, ld, exps);
-    dim3 grid((unsigned)((kp + 255) / 256), (unsigned)rows);
+    const long ksteps = kp / 32, rows_p = (rows + 127) / 128 * 128;
+    dim3 grid((unsigned)((2 * ksteps + 127) / 128), (unsigned)rows_p);
     switch (slices) {
-        case 4: ozaki::slice_rows_kernel<4><<<grid, 256, 0, s>>>(A, rows, cols, ld, exps, out, kp); break;
-        case 5: ozaki::slice_rows_kernel<5><<<grid, 256, 0, s>>>(A, rows, cols, ld, exps, out, kp); break;
-        case 6: ozaki::slice_rows_kernel<6><<<grid, 256, 0, s>>>(A, rows, cols, ld, exps, out, kp); break;
+        case 4: ozaki::slice_rows_tiled_kernel<4><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps); break;
+        case 5: ozaki::slice_rows_tiled_kernel<5><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps); break;
+        case 6: ozaki::slice_rows_tiled_kernel<6><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -349,13 +398,13 @@ cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStre
     P.t8 = a.t8; P.t_exp = a.t_exp; P.L = a.L; P.Pt = a.Pt;
     P.ext = a.ext; P.C0 = a.C0; P.kp = a.kp; P.ldp = a.ldp; P.ncp = a.ncp;
     P.Ns = a.Ns; P.ncol = a.ncol; P.c0 = a.c0;
-    P.chunk = slices <= 5 ? 8192 : 4096;       // int32 overflow bound per significance level (see header comment)
+    P.chunk = 16384;       // int32 overflow bound: level S-1 sums S products of balanced digits, S * 2^14 * chunk < 2^31 for S <= 7
     P.n_stile = (a.Ns + 127) / 128;
     P.n_itile = 0;
     switch (slices) {
-        case 4: return ozaki::launch_one<4, 128>(P, sm_count, s);
-        case 5: return ozaki::launch_one<5, 96>(P, sm_count, s);
-        case 6: return ozaki::launch_one<6, 80>(P, sm_count, s);
+        case 4: return ozaki::launch_one<4>(P, sm_count, s);
+        case 5: return ozaki::launch_one<5>(P, sm_count, s);
+        case 6: return ozaki::launch_one<6>(P, sm_count, s);
     }
     return cudaErrorInvalidValue;
 }

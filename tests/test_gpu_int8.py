@@ -1,0 +1,84 @@
+"""GPU parity tests of the tcgen05 int8 digit-slice projection (settings key ``precision: int8x5 | int8x6``).
+
+The slice path computes Pt = A.K as an exact integer product of fixed-point operands (39 / 47 bits, balanced
+digits, one exponent per sensor row and per covariance table); everything after it is the fp64 path.  Stated
+tolerance: 1e-5 norm-wise (max|delta| / max|ref| per cube) on posterior mean and variance -- the north star's
+figure; measured errors are 1e-8 .. 1e-11 and the assertions below are tighter than the stated tolerance.
+"""
+import numpy as np
+import pytest
+
+from conftest import CUBES, load_golden, normwise_err
+from oracle import numpy_oracle as o
+from test_gpu_parity import base_cfg, configure, ctx, run_cubing, synthetic_inputs  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+TOL_STATED = 1e-5
+
+
+@pytest.mark.parametrize("which,prec", [("1", "int8x5"), ("1", "int8x6"), ("2", "int8x6")])
+def test_int8_examples_vs_committed_vtk_goldens(ctx, which, prec):
+    """The reference's own golden cubes (25x16x16, sparse kernel) through the tensor-core slice path."""
+    f = load_golden("example%s.npz" % which)
+    configure(f["cfg"], precision=prec)
+    inv, out = run_cubing(f)
+    for n, a in zip(CUBES, out):
+        assert normwise_err(a, f["gold_" + n]) < 1e-6 < TOL_STATED, n
+    assert abs(inv.logl - float(f["logl"])) < 1e-3
+
+
+@pytest.mark.parametrize("shape,kf,nd", [((5, 3, 16), "exp", 3), ((9, 7, 16), "sparse", 4), ((6, 5, 32), "matern32", 5),
+                                         ((16, 16, 16), "exp", 50), ((11, 4, 48), "exp", 0)])
+@pytest.mark.parametrize("prec", ["int8x5", "int8x6"])
+def test_int8_cubing_vs_oracle(ctx, shape, kf, nd, prec):
+    """Ragged sensor-row / voxel-column tiles (Ns and N not multiples of 128 / 80 / 96), all kernels, nd = 0 and > 0."""
+    c = configure(base_cfg(), xNcube=shape[0], yNcube=shape[1], zNcube=shape[2], kernelfunc=kf, precision=prec)
+    f = synthetic_inputs(c, nd)
+    gl = c.gp_lengthscale * c.xvoxsize * (np.array([1.0, 1.01, 1.02]) if kf == "matern32" else np.ones(3))
+    with np.errstate(all="ignore"):
+        ref, ex = o.cubing_lean(c, f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"], gp_length=gl.copy())
+    inv, out = run_cubing(f, gl=gl.copy())
+    tol = 1e-6 if prec == "int8x5" else 1e-7
+    for n, a, r in zip(CUBES, out, ref):
+        assert normwise_err(a, r) < tol < TOL_STATED, n
+    assert abs(inv.logl - ex["logl"]) < 1e-5 * abs(ex["logl"])
+
+
+def test_int8_needs_z_multiple_of_16(ctx):
+    """The Toeplitz digit generation works on 16-voxel z segments: other cubes are refused loudly (no silent fallback)."""
+    c = configure(base_cfg(), xNcube=6, yNcube=5, zNcube=12, kernelfunc="exp", precision="int8x6")
+    f = synthetic_inputs(c, 2)
+    with pytest.raises(Exception) as e:
+        run_cubing(f)
+    assert "zNcube" in str(e.value)
+
+
+def test_int8_full_size_32cube_vs_fp64_path(ctx):
+    """BASELINE config 2 size (N = 32768, M = 2048, exp kernel, cond ~ 1e6): slice path against the fp64 DMMA path
+    on the same device problem, plus linearity of the mean in the data."""
+    from geobo_b200 import _lib
+    c = configure(base_cfg(), xNcube=32, yNcube=32, zNcube=32, kernelfunc="exp")
+    E, vp = o.cube_geometry(c)
+    loc = o.sensor_grid(c)
+    prob = _lib.Problem(ctx, (32, 32, 32), (c.xvoxsize, c.yvoxsize, c.zvoxsize), E, loc, c.magneticField,
+                        c.c_MILLIGALS_UNITS, c.fcor_grav, 1.0, c.fcor_mag, np.zeros(0, dtype=np.int64))
+    gl = c.gp_lengthscale * c.xvoxsize * np.array([1.0, 1.02, 1.0])
+    rng = np.random.default_rng(5)
+    y1, y2 = rng.standard_normal(prob.M), rng.standard_normal(prob.M)
+    prob.set_data(y1)
+    mu0, var0, logl0, info0 = prob.predict(prob.hyper(gl, c.gp_err, c.gp_coeff, 1.0, "exp"))
+    h6 = prob.hyper(gl, c.gp_err, c.gp_coeff, 1.0, "exp", slices=6)
+    mu1, var1, logl1, info1 = prob.predict(h6)
+    assert info0 == 0 and info1 == 0
+    assert np.abs(mu1 - mu0).max() < 1e-6 * np.abs(mu0).max()
+    assert np.abs(var1 - var0).max() < 1e-6 * np.abs(var0).max()
+    assert abs(logl1 - logl0) < 1e-6 * abs(logl0)
+    prob.set_data(y2)
+    mu2, var2, _, _ = prob.predict(h6)
+    prob.set_data(2.0 * y1 - 0.5 * y2)
+    mu3, var3, _, _ = prob.predict(h6)
+    scale = max(np.abs(mu1).max(), np.abs(mu2).max())
+    assert np.abs(mu3 - (2.0 * mu1 - 0.5 * mu2)).max() < 1e-8 * scale
+    assert np.array_equal(var1, var2)
+    prob.close()

@@ -13,6 +13,10 @@ def main():
     cases = [((8, 6, 16), "exp", 5), ((12, 10, 16), "matern32", 7), ((16, 16, 16), "sparse", 50)]
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         cases = [((32, 32, 32), "exp", 0), ((32, 32, 32), "matern32", 50)]
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg3":
+        cases = [((64, 64, 32), "matern32", 50)]
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg3e":
+        cases = [((64, 64, 32), "exp", 0)]
     ctx = _lib.default_context()
     for shape, kf, nd in cases:
         cfg = synth.settings(*shape, kernelfunc=kf)
