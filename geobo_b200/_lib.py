@@ -34,7 +34,7 @@ class ProblemDesc(C.Structure):
 
 class Hyper(C.Structure):
     _fields_ = [("gp_length", C.c_double * 3), ("gp_sigma", C.c_double * 3), ("coeffm", C.c_double * 3),
-                ("gp_amp", C.c_double), ("kernel_id", C.c_int), ("slices", C.c_int)]
+                ("gp_amp", C.c_double), ("kernel_id", C.c_int), ("slices", C.c_int), ("refine", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol here is declared in include/geobo_b200.h
@@ -249,7 +249,7 @@ class Problem:
         self.ctx.check(self.lib.gb_problem_set_data(self.h, _ptr(y)))
 
     @staticmethod
-    def hyper(gp_length, gp_sigma, coeffm, gp_amp, kernel, slices=0):
+    def hyper(gp_length, gp_sigma, coeffm, gp_amp, kernel, slices=0, refine=1):
         h = Hyper()
         h.gp_length[:] = [float(v) for v in gp_length]
         h.gp_sigma[:] = [float(v) for v in gp_sigma]
@@ -259,6 +259,7 @@ class Problem:
             raise ValueError("kernelfunc must be one of %s, got %r" % (sorted(KERNEL_IDS), kernel))
         h.kernel_id = KERNEL_IDS[kernel]
         h.slices = int(slices)
+        h.refine = int(refine)
         return h
 
     def predict(self, hyper, want_host=True, flags=FLAG_ALL):

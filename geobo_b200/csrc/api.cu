@@ -252,6 +252,23 @@ struct gb_problem {
     uint8_t* t8 = nullptr;
     int* t_exp = nullptr;
     int a8_slices = 0;
+    // int8 variance path: explicit Linv, its digit blocks, transposed digit blocks of Pt, per-row-tile column sums of squares
+    double* Linv = nullptr;              // [Mp][Mp]
+    double* tmpL = nullptr;              // [128][Mp]
+    double* alpha = nullptr;             // [Mp]  (A K A^T + Sigma)^-1 y
+    uint8_t* l8 = nullptr;
+    int* l_exp = nullptr;
+    uint8_t* b8 = nullptr;
+    int* b_exp = nullptr;
+    double* partial = nullptr;           // [Mp/128][ldp]
+    int var_slices = 0;
+    size_t b8_bytes = 0;
+    // fp64 matrix-free refinement scratch
+    double* rf_w = nullptr;              // [3][Kp]   A3^T alpha
+    double* rf_z = nullptr;              // [3][ncp]  K w on this rank's voxel columns
+    double* rf_part = nullptr;           // [8][2][Kp]
+    double* rf_t = nullptr;              // [Mp] x 3: t, r, tmp
+    long nlaunch = 0;
     double* y_host_pinned = nullptr;
     double* out_pinned = nullptr;        // [6*ncol + 4]
     cudaEvent_t ev[GB_NUM_TIMERS + 1];
@@ -277,6 +294,8 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
     cudaStreamSynchronize(p->ctx->stream);
     void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
                     p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp,
+                    p->Linv, p->tmpL, p->alpha, p->l8, p->l_exp, p->b8, p->b_exp, p->partial,
+                    p->rf_w, p->rf_z, p->rf_part, p->rf_t,
                     p->linv, p->scal, p->info, p->mu, p->var};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -468,6 +487,11 @@ __global__ void dot_self_kernel(const double* __restrict__ ysol, long M, double*
     if (threadIdx.x == 0) *out = red[0];
 }
 
+__global__ void set_identity_kernel(double* __restrict__ X, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) X[i * n + i] = 1.0;
+}
+
 static gemm::Task mk(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int M, int N, int K, int lower) {
     gemm::Task t;
     memset(&t, 0, sizeof t);
@@ -482,6 +506,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     cudaStream_t s = ctx->stream;
     if (!p->have_data) return gb_fail(ctx, GB_ERR_ARG, "gb_predict before gb_problem_set_data");
     p->last_full = full;
+    p->nlaunch = 0;
     CovParams cp;
     GB_TRY(fill_cov_params(ctx, cp, h->kernel_id, h->gp_length, h->coeffm, h->gp_amp));
     GB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -521,6 +546,16 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
             if (p->t8) { cudaFree(p->t8); p->t8 = nullptr; }
             GB_CUDA(ctx, cudaMalloc((void**)&p->t8, (size_t)ozaki_table_bytes(p->ext, S)));
             if (!p->t_exp) GB_CUDA(ctx, cudaMalloc((void**)&p->t_exp, 16 * sizeof(int)));
+            // digit scratch shared by the AkA products (row digits of three Pt blocks) and the variance product
+            // (transposed digits of all of Pt): the two uses are sequential
+            if (p->b8) { cudaFree(p->b8); p->b8 = nullptr; }
+            if (p->b_exp) { cudaFree(p->b_exp); p->b_exp = nullptr; }
+            const size_t aka_bytes = 3 * (size_t)ozaki_rows_bytes(Ns, ncp, S, ozaki_tile_n(S));
+            const size_t var_bytes = (size_t)ozaki_cols_bytes(ldp, Mp, S);
+            p->b8_bytes = aka_bytes > var_bytes ? aka_bytes : var_bytes;
+            GB_CUDA(ctx, cudaMalloc((void**)&p->b8, p->b8_bytes));
+            GB_CUDA(ctx, cudaMalloc((void**)&p->b_exp, (size_t)(ldp > 3 * Ns ? ldp : 3 * Ns) * sizeof(int)));
+            p->bytes += 2 * (size_t)ozaki_rows_bytes(Ns, p->Kp, S) + p->b8_bytes;
             p->a8_slices = S;
         }
         GB_CUDA(ctx, ozaki_slice_tables(p->tables, p->ext, S, p->t_exp, p->t8, s));
@@ -530,6 +565,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         oa.ext = p->ext; oa.C0 = p->C0; oa.kp = p->Kp; oa.ldp = ldp; oa.ncp = ncp;
         oa.Ns = (int)Ns; oa.ncol = (int)ncol; oa.c0 = (int)p->c0;
         GB_CUDA(ctx, ozaki_project(oa, S, ctx->sm_count, s));
+        p->nlaunch += 2;                  // table slicing (absmax + digits)
     } else {
         gemm::TaskBatch b;
         b.n = 0;
@@ -552,7 +588,27 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     GB_CUDA(ctx, cudaEventRecord(p->ev[3], s));
 
     // ---- AkA = A3 . Pt^T (lower triangle) over this rank's voxel columns
-    {
+    if (h->slices != 0) {
+        // int8 digit products: the sensitivities' digit blocks are reused (K steps c0/32 ..), the three Pt blocks
+        // (rows c', columns r = c) are sliced row-wise into N-side digit blocks
+        const int S = h->slices, NT = ozaki_tile_n(S);
+        const size_t blk = (size_t)ozaki_rows_bytes(Ns, ncp, S, NT);
+        const int a_ksteps = (int)(p->Kp / 32), a_k0 = (int)(p->c0 / 32), ks = (int)(ncp / 32);
+        const int cc[3][2] = {{0, 0}, {1, 0}, {1, 1}};      // (c, c'): block row = A_c, block column = Pt rows of c'
+        for (int t = 0; t < 3; ++t) {
+            const int c = cc[t][0], cp_ = cc[t][1];
+            GB_CUDA(ctx, ozaki_slice_rows(p->Pt + (long)cp_ * Ns * ldp + (long)c * ncp, Ns, ncp, ldp, S, p->b_exp + t * Ns, p->b8 + t * blk, ncp, NT, s));
+            GB_CUDA(ctx, ozaki_gemm_store(p->a8[c], p->a_exp[c], a_ksteps, a_k0, p->b8 + t * blk, p->b_exp + t * Ns, ks, 0, ks, (int)Ns, (int)Ns,
+                                          p->Bm + (long)c * Ns * Mp + (long)cp_ * Ns, Mp, c == cp_ ? 1 : 0, S, ctx->sm_count, s));
+        }
+        p->nlaunch += 8;
+        if (p->nd) {
+            dim3 grid((unsigned)((M + 255) / 256), (unsigned)p->nd);
+            drill_rows_aka_kernel<<<grid, 256, 0, s>>>(p->Pt, ldp, ncp, p->drill_dev, p->c0, p->c1, 2 * Ns, M, p->Bm, Mp);
+            GB_CUDA(ctx, cudaGetLastError());
+        }
+    } else {
+
         gemm::TaskBatch b;
         b.n = 3;
         b.t[0] = mk(p->A[0] + p->c0, p->lda, p->Pt, ldp, p->Bm, Mp, (int)Ns, (int)Ns, (int)ncp, 1);
@@ -579,13 +635,75 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->ysol, 16, 1, p->ytmp, s));
     dot_self_kernel<<<1, 256, 0, s>>>(p->ysol, M, p->scal + 1);
     GB_CUDA(ctx, cudaGetLastError());
-    if (full) {
+    const bool int8_var = full && h->slices != 0 && Mp <= 16384;
+    if (int8_var) {
+        // ---- variance and mean without ever forming V = L^-1 Pt (:114-117) in memory:
+        //   Linv = L^-1 explicitly (fp64 blocked solve against the identity), alpha = Linv^T u,
+        //   one pass over Pt: transposed digit blocks + mu = Pt^T alpha (:115),
+        //   colsumsq(Linv . Pt) on the int8 tensor cores with the reduction in the epilogue (:117, diag only).
+        const int S = h->slices;
+        if (p->var_slices != S) {
+            if (p->l8) { cudaFree(p->l8); p->l8 = nullptr; }
+            if (!p->Linv) {
+                GB_CUDA(ctx, cudaMalloc((void**)&p->Linv, (size_t)Mp * Mp * sizeof(double)));
+                GB_CUDA(ctx, cudaMalloc((void**)&p->tmpL, (size_t)128 * Mp * sizeof(double)));
+                GB_CUDA(ctx, cudaMalloc((void**)&p->alpha, (size_t)Mp * sizeof(double)));
+                GB_CUDA(ctx, cudaMalloc((void**)&p->l_exp, (size_t)Mp * sizeof(int)));
+                GB_CUDA(ctx, cudaMalloc((void**)&p->partial, (size_t)(Mp / 128) * ldp * sizeof(double)));
+                GB_CUDA(ctx, cudaMalloc((void**)&p->rf_w, (size_t)3 * p->Kp * sizeof(double)));
+                GB_CUDA(ctx, cudaMalloc((void**)&p->rf_z, (size_t)3 * ncp * sizeof(double)));
+                GB_CUDA(ctx, cudaMalloc((void**)&p->rf_part, (size_t)16 * p->Kp * sizeof(double)));
+                GB_CUDA(ctx, cudaMalloc((void**)&p->rf_t, (size_t)3 * Mp * sizeof(double)));
+                GB_CUDA(ctx, cudaMemsetAsync(p->rf_t, 0, (size_t)3 * Mp * sizeof(double), s));
+                p->bytes += (size_t)Mp * Mp * 8 + (size_t)128 * Mp * 8 + (size_t)(Mp / 128) * ldp * 8;
+            }
+            GB_CUDA(ctx, cudaMalloc((void**)&p->l8, (size_t)ozaki_rows_bytes(Mp, Mp, S)));
+            p->bytes += (size_t)ozaki_rows_bytes(Mp, Mp, S);
+            p->var_slices = S;
+        }
+        GB_CUDA(ctx, cudaMemsetAsync(p->Linv, 0, (size_t)Mp * Mp * sizeof(double), s));
+        set_identity_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(p->Linv, Mp);
+        GB_CUDA(ctx, cudaGetLastError());
+        GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->Linv, Mp, (int)Mp, p->tmpL, s, 1));
+        // alpha = L^-T u, then refined against the fp64 matrix-free operator (the factor came from digit-rounded operands)
+        GB_CUDA(ctx, refine_linv_t(p->Linv, Mp, p->ysol, 16, p->alpha, s));
+        RefineArgs ra;
+        ra.A[0] = p->A[0]; ra.A[1] = p->A[1]; ra.tables = p->tables; ra.drill = p->drill_dev; ra.partial = p->rf_part;
+        ra.Ns = Ns; ra.N = p->N; ra.lda = p->lda; ra.Kp = p->Kp; ra.ext = p->ext; ra.C0 = p->C0; ra.nd = p->nd;
+        ra.c0 = p->c0; ra.ncol = ncol; ra.ncp = ncp;
+        ra.n[0] = (int)p->n[0]; ra.n[1] = (int)p->n[1]; ra.n[2] = (int)p->n[2];
+        ra.nsplit = 8;
+        double* rt = p->rf_t;           // t = A3 K A3^T alpha
+        double* rr = p->rf_t + Mp;      // residual
+        double* rtmp = p->rf_t + 2 * Mp;
+        const int nref = h->refine < 0 ? 0 : h->refine;
+        for (int itr = 0; itr <= nref; ++itr) {
+            GB_CUDA(ctx, refine_at_alpha(ra, p->alpha, p->rf_w, s));       // w = A3^T alpha
+            GB_CUDA(ctx, refine_kw(ra, p->rf_w, p->rf_z, s));              // z = K w   (this rank's voxel columns)
+            p->nlaunch += 3 + (p->nd ? 1 : 0);
+            if (itr == nref) break;                                        // z = K A3^T alpha = posterior mean
+            GB_CUDA(ctx, refine_a_z(ra, p->rf_z, rt, s));                  // t = A3 z  (partial over this rank's columns)
+            GB_TRY(comm_allreduce_sum_f64(ctx, rt, (size_t)Mp));
+            GB_CUDA(ctx, refine_residual(p->ydev, rt, p->alpha, Ns, M, Mp, h->gp_sigma, rr, s));
+            GB_CUDA(ctx, refine_apply_inverse(p->Linv, Mp, rr, rtmp, p->alpha, 1, s));   // alpha += L^-T L^-1 r
+            p->nlaunch += 4 + (p->nd ? 1 : 0);
+        }
+        GB_CUDA(ctx, refine_scatter_mu(p->rf_z, ncp, ncol, p->mu, s));
+        if (nref > 0) GB_CUDA(ctx, refine_dot(p->ydev, p->alpha, M, p->scal + 1, s));    // u.u = y^T (AkA)^-1 y with the refined alpha
+        GB_CUDA(ctx, ozaki_slice_sens(p->Linv, Mp, Mp, Mp, S, p->l_exp, p->l8, Mp, s));
+        GB_CUDA(ctx, ozaki_slice_cols_mean(p->Pt, Mp, ldp, ldp, S, p->b_exp, p->b8, p->alpha, nullptr, ncp, ncol, s));
+        GB_CUDA(ctx, ozaki_colsumsq_tri(p->l8, p->l_exp, p->b8, p->b_exp, (int)Mp, ldp, S, p->partial, ctx->sm_count, s));
+        GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
+        GB_CUDA(ctx, ozaki_var_finalize(p->partial, (int)(Mp / 128), ldp, ncp, ncol, h->gp_amp, p->var, s));
+        p->nlaunch += 2 * (Mp / 128) + 8;
+    } else if (full) {
         // ---- V = L^-1 Pt (:114) in place, then mean (:115) and variance diagonal (:117)
         GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->Pt, ldp, (int)ldp, p->tmp, s));
         GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
         dim3 grid((unsigned)((ncp + 255) / 256), 3);
         mean_var_kernel<<<grid, 256, 0, s>>>(p->Pt, ldp, ncp, ncol, M, p->ysol, h->gp_amp, p->mu, p->var);
         GB_CUDA(ctx, cudaGetLastError());
+        p->nlaunch += 2 * (Mp / 128) + 1;
     } else {
         GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
     }
@@ -605,12 +723,11 @@ static int collect_timings(gb_problem* p) {
     GB_CUDA(ctx, cudaEventElapsedTime(&t, p->ev[0], p->ev[8]));
     p->ms[GB_T_TOTAL] = t;
     {
-        // kernels launched by run_predict: tables, set_y, project, [drill rows x2], aka, noise diag,
-        // Cholesky (potrf + panel + trailing per block), two blocked solves (2 GEMMs per block), dot, mean/var
+        // kernels launched by run_predict: set_y, tables, projection (+ digit slicing), [drill rows x2], aka, noise diag,
+        // Cholesky (potrf + panel + trailing per block), u solve (2 GEMMs per block), dot; the mean / variance
+        // stage adds its own count (p->nlaunch) in run_predict
         const long nblk = p->Mp / 128;
-        long n = 5 + (p->nd ? 2 : 0) + (3 * nblk - 2) + 2 * nblk + 1;
-        if (p->last_full) n += 2 * nblk + 1;
-        p->ms[GB_T_LAUNCHES] = (double)n;
+        p->ms[GB_T_LAUNCHES] = (double)(5 + (p->nd ? 2 : 0) + (3 * nblk - 2) + 2 * nblk + 1 + p->nlaunch);
     }
     return GB_OK;
 }
@@ -720,7 +837,9 @@ extern "C" int gb_posterior_cov(gb_problem* p, const gb_hyper* h, double* out) {
     gb_ctx* ctx = p->ctx;
     if (p->ncol != p->N) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "gb_posterior_cov needs an unsharded problem");
     if (3 * p->N > 46000) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "dense 3N x 3N posterior covariance refused for N=%lld", (long long)p->N);
-    GB_TRY(run_predict(p, h, true));
+    gb_hyper h64 = *h;
+    h64.slices = 0;                       // the dense posterior covariance is built from V = L^-1 Pt, which only the fp64 path stores
+    GB_TRY(run_predict(p, &h64, true));
     const long n3 = 3 * p->N;
     DevBuf<double> o;
     GB_CUDA(ctx, o.alloc((size_t)n3 * n3));

@@ -176,12 +176,13 @@ cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork&
     return cudaSuccess;
 }
 
-cudaError_t chol_forward_solve(const double* L, long ldl, int Mp, const CholWork& w, double* Pt, long ldp, int ncols,
-                               double* tmp, cudaStream_t s) {
+cudaError_t chol_forward_solve(const double* L, long ldl, int Mp, const CholWork& w, double* Pt, long ldp, int ncols_all,
+                               double* tmp, cudaStream_t s, int tri) {
     const int nblk = Mp / NB;
     cudaError_t e;
     for (int kb = 0; kb < nblk; ++kb) {
         const int k0 = kb * NB;
+        const int ncols = tri ? (ncols_all < k0 + NB ? ncols_all : k0 + NB) : ncols_all;
         double* rowblk = Pt + (long)k0 * ldp;
         // tmp = Pt[kb] - L[kb, 0:k0] . V[0:k0]
         gemm::TaskBatch a;

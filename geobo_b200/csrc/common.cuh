@@ -130,11 +130,44 @@ struct OzakiArgs {
 };
 int ozaki_tile_n(int slices);
 long ozaki_table_bytes(long ext, int slices);
-long ozaki_rows_bytes(long rows, long kp, int slices);
+long ozaki_rows_bytes(long rows, long kp, int slices, int tr = 128);
+cudaError_t ozaki_slice_rows(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp, int tr,
+                             cudaStream_t s);
 cudaError_t ozaki_slice_sens(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp,
                              cudaStream_t s);
 cudaError_t ozaki_slice_tables(const double* tables, long ext, int slices, int* exps, uint8_t* out, cudaStream_t s);
 cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStream_t s);
+// int8 digit-slice GEMM with both operands in memory (ozaki_gemm.cu)
+long ozaki_cols_bytes(long cols, long kp, int slices);
+cudaError_t ozaki_slice_cols_mean(const double* X, long rows, long cols, long ld, int slices, int* exps, uint8_t* out,
+                                  const double* alpha, double* mu, long ncp, long ncol, cudaStream_t s);
+cudaError_t ozaki_colsumsq_tri(const uint8_t* a8, const int* a_exp, const uint8_t* b8, const int* b_exp, int Mp, long ncols,
+                               int slices, double* partial, int sm_count, cudaStream_t s);
+cudaError_t ozaki_gemm_store(const uint8_t* a8, const int* a_exp, int a_ksteps, int a_k0, const uint8_t* b8, const int* b_exp,
+                             int b_ksteps, int b_k0, int ksteps, int M, int N, double* C, long ldc, int lower, int slices,
+                             int sm_count, cudaStream_t s);
+cudaError_t ozaki_var_finalize(const double* partial, int n_mtile, long ldpart, long ncp, long ncol, double amp, double* var,
+                               cudaStream_t s);
+
+// fp64 matrix-free operator pieces for the iterative refinement of alpha and the posterior mean (refine.cu)
+struct RefineArgs {
+    const double* A[2];      // [Ns][lda]
+    const double* tables;    // [9][ext]
+    const int64_t* drill;    // [nd] (device)
+    double* partial;         // [nsplit][2][Kp] scratch of A3^T alpha
+    long Ns, N, lda, Kp, ext, C0, nd, c0, ncol, ncp;
+    int n[3];
+    int nsplit;
+};
+cudaError_t refine_at_alpha(const RefineArgs& a, const double* alpha, double* w /*[3][Kp]*/, cudaStream_t s);
+cudaError_t refine_kw(const RefineArgs& a, const double* w, double* z /*[3][ncp]*/, cudaStream_t s);
+cudaError_t refine_a_z(const RefineArgs& a, const double* z, double* t /*[Mp]*/, cudaStream_t s);
+cudaError_t refine_residual(const double* y, const double* t, const double* alpha, long Ns, long M, long Mp, const double sigma[3],
+                            double* r, cudaStream_t s);
+cudaError_t refine_apply_inverse(const double* Linv, long Mp, const double* x, double* tmp, double* out, int accumulate, cudaStream_t s);
+cudaError_t refine_linv_t(const double* Linv, long Mp, const double* x, int xs, double* out, cudaStream_t s);
+cudaError_t refine_dot(const double* a, const double* b, long n, double* out, cudaStream_t s);
+cudaError_t refine_scatter_mu(const double* z, long ncp, long ncol, double* mu, cudaStream_t s);
 
 // Cholesky / triangular solve (chol.cu)
 struct CholWork {
@@ -144,5 +177,6 @@ struct CholWork {
 };
 cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, cudaStream_t s);
 // V = L^-1 Pt in place (Pt: [Mp][ldp]); tmp: [128][ldp]
+// tri != 0: the right-hand side is lower triangular (e.g. the identity): block row kb only has columns < 128 (kb + 1)
 cudaError_t chol_forward_solve(const double* L, long ldl, int Mp, const CholWork& w, double* Pt, long ldp, int ncols,
-                               double* tmp, cudaStream_t s);
+                               double* tmp, cudaStream_t s, int tri = 0);

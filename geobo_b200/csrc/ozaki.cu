@@ -26,54 +26,11 @@
 // Stage hand-off is mbarrier based (full: producer warp + bulk-copy bytes -> MMA, empty: tcgen05.commit -> producer).
 #include "common.cuh"
 #include "umma.cuh"
+#include "ozaki.cuh"
 
 using namespace umma;
 
 namespace ozaki {
-
-constexpr int TABLE_PAD = 64;
-__host__ __device__ constexpr long plane_stride(long ext) { return (ext + TABLE_PAD + 15) & ~15L; }   // keeps every digit plane 16-byte aligned
-
-// Tile shape per slice count: the S accumulators of one 128 x NT tile fill TMEM (S * NT <= 512 columns);
-// W producer warps, STAGES (multiple of W) shared-memory stages of S * (4096 + NT * 32) bytes.
-template <int S> struct Cfg;
-template <> struct Cfg<4> { static constexpr int NT = 128, W = 6, STAGES = 6; };
-template <> struct Cfg<5> { static constexpr int NT = 96, W = 6, STAGES = 6; };
-template <> struct Cfg<6> { static constexpr int NT = 80, W = 5, STAGES = 5; };
-
-// ------------------------------------------------------------------------------------------------ digit extraction
-// t in [-1/2, 1/2]: BALANCED digits (every d_q in [-128, 127], stored as two's-complement bytes) of t rounded to
-// nearest at the last digit:  t ~ sum_q d_q 2^-(7 + 8 q).  All digits signed => one instruction descriptor for every
-// digit pair, several B digits can share one wide-N MMA, and the worst-case accumulator growth is 4x smaller.
-template <int S>
-__device__ __forceinline__ void digits(double t, uint8_t (&d)[S]) {
-    t += ldexp(1.0, -(7 + 8 * (S - 1) + 1));
-    int v[S];
-    double x = t * 128.0;
-    double f = floor(x);
-    v[0] = (int)f;                       // in [-64, 64]
-    double r = x - f;
-#pragma unroll
-    for (int q = 1; q < S; ++q) {
-        x = r * 256.0;
-        f = floor(x);
-        v[q] = (int)f;                   // in [0, 255]
-        r = x - f;
-    }
-#pragma unroll
-    for (int q = S - 1; q >= 1; --q)
-        if (v[q] >= 128) { v[q] -= 256; v[q - 1] += 1; }
-#pragma unroll
-    for (int q = 0; q < S; ++q) d[q] = (uint8_t)(int8_t)v[q];
-}
-
-// exponent e with |x| <= 2^(e-1)  (so t = x / 2^e lies in [-1/2, 1/2])
-__device__ __forceinline__ int scale_exp(double amax) {
-    if (!(amax > 0.0) || !isfinite(amax)) return 0;
-    int e;
-    frexp(amax, &e);      // amax = m 2^e, m in [0.5, 1)
-    return e + 1;
-}
 
 __global__ void row_absmax_kernel(const double* __restrict__ A, long rows, long cols, long ld, int* __restrict__ exps) {
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -86,11 +43,12 @@ __global__ void row_absmax_kernel(const double* __restrict__ A, long rows, long 
     if (lane == 0) exps[row] = scale_exp(m);
 }
 
-// A (rows x ld fp64, cols valid) -> pre-tiled digit blocks [row tile][k step][digit][4096 B canonical layout];
+// A (rows x ld fp64, cols valid) -> pre-tiled digit blocks [row tile of TR rows][k step][digit][TR x 32 B canonical layout];
 // one thread per (row, 16 consecutive contraction indices): S 16-byte stores.  Rows >= rows and columns >= cols are zero.
+// TR = 128 for an M-side (A) operand, TR = NT for an N-side (B) operand.
 template <int S>
 __global__ void slice_rows_tiled_kernel(const double* __restrict__ A, long rows, long cols, long ld, const int* __restrict__ exps,
-                                        uint8_t* __restrict__ out, long ksteps) {
+                                        uint8_t* __restrict__ out, long ksteps, int TR) {
     const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;    // 16-column group
     const long row = blockIdx.y;
     if (g >= 2 * ksteps) return;
@@ -110,11 +68,12 @@ __global__ void slice_rows_tiled_kernel(const double* __restrict__ A, long rows,
             }
         }
     }
-    const long stile = row >> 7, ks = g >> 1;
-    const uint32_t off = core_offset((uint32_t)(row & 127), (uint32_t)(g & 1));
+    const long tile = row / TR, ks = g >> 1;
+    const long blk = (long)TR * 32;
+    const uint32_t off = core_offset((uint32_t)(row % TR), (uint32_t)(g & 1));
 #pragma unroll
     for (int q = 0; q < S; ++q)
-        *reinterpret_cast<uint4*>(out + ((stile * ksteps + ks) * S + q) * 4096 + off) = make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
+        *reinterpret_cast<uint4*>(out + ((tile * ksteps + ks) * S + q) * blk + off) = make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
 }
 
 __global__ void table_absmax_kernel(const double* __restrict__ tab, long ext, int* __restrict__ exps) {
@@ -362,20 +321,24 @@ static cudaError_t launch_one(const Params& P, int sm_count, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------ host entry points
 int ozaki_tile_n(int slices) { return slices == 4 ? ozaki::Cfg<4>::NT : slices == 5 ? ozaki::Cfg<5>::NT : slices == 6 ? ozaki::Cfg<6>::NT : 0; }
 
-// bytes of the pre-tiled digit blocks of a rows x kp operand
-long ozaki_rows_bytes(long rows, long kp, int slices) { return ((rows + 127) / 128) * (kp / 32) * (long)slices * 4096; }
+// bytes of the pre-tiled digit blocks of a rows x kp operand with `tr` rows per tile (128: M side, tile_n: N side)
+long ozaki_rows_bytes(long rows, long kp, int slices, int tr) { return ((rows + tr - 1) / tr) * (kp / 32) * (long)slices * tr * 32; }
 
-cudaError_t ozaki_slice_sens(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp, cudaStream_t s) {
+cudaError_t ozaki_slice_rows(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp, int tr, cudaStream_t s) {
     ozaki::row_absmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(A, rows, cols, ld, exps);
-    const long ksteps = kp / 32, rows_p = (rows + 127) / 128 * 128;
+    const long ksteps = kp / 32, rows_p = (rows + tr - 1) / tr * tr;
     dim3 grid((unsigned)((2 * ksteps + 127) / 128), (unsigned)rows_p);
     switch (slices) {
-        case 4: ozaki::slice_rows_tiled_kernel<4><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps); break;
-        case 5: ozaki::slice_rows_tiled_kernel<5><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps); break;
-        case 6: ozaki::slice_rows_tiled_kernel<6><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps); break;
+        case 4: ozaki::slice_rows_tiled_kernel<4><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr); break;
+        case 5: ozaki::slice_rows_tiled_kernel<5><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr); break;
+        case 6: ozaki::slice_rows_tiled_kernel<6><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
+}
+
+cudaError_t ozaki_slice_sens(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp, cudaStream_t s) {
+    return ozaki_slice_rows(A, rows, cols, ld, slices, exps, out, kp, 128, s);
 }
 
 cudaError_t ozaki_slice_tables(const double* tables, long ext, int slices, int* exps, uint8_t* out, cudaStream_t s) {

@@ -75,8 +75,10 @@ class Inversion:
     def _slices():
         """Optional settings key ``precision`` (absent in reference YAMLs -> 'fp64'):
         'fp64'   : projection A.K on the fp64 tensor pipe (DMMA);
-        'int8x4' / 'int8x5' / 'int8x6' : error-free int8 digit products on tcgen05/TMEM with 31 / 39 / 47 bits per
-        operand (everything after the projection stays fp64).  Needs zNcube % 16 == 0."""
+        'int8x4' / 'int8x5' / 'int8x6' : exact int8 digit products on tcgen05/TMEM with 31 / 39 / 47 bits per
+        operand for the three dense products (A.K, A.Pt^T, L^-1.Pt); the Cholesky stays fp64 and the mean comes from
+        ``refine`` (optional key, default 1) steps of iterative refinement against the fp64 matrix-free operator.
+        Needs zNcube % 16 == 0."""
         prec = str(getattr(_cfg, "precision", "fp64")).lower()
         if prec in ("fp64", "f64", "double"):
             return 0
@@ -87,7 +89,8 @@ class Inversion:
     def _hyper(self, gp_length=None, coeffm=None, gp_amp=None):
         return _lib.Problem.hyper(self.gp_length if gp_length is None else gp_length, self.gp_sigma,
                                   self.coeffm if coeffm is None else coeffm,
-                                  self.gp_amp if gp_amp is None else gp_amp, _cfg.kernelfunc, self._slices())
+                                  self.gp_amp if gp_amp is None else gp_amp, _cfg.kernelfunc, self._slices(),
+                                  int(getattr(_cfg, "refine", 1)))
 
     def _build_problem(self):
         if not hasattr(self, "Edges"):

@@ -139,6 +139,9 @@ typedef struct gb_hyper {
     int kernel_id;             /* GB_KERNEL_*                                              */
     int slices;                /* 0: fp64 tensor pipe (DMMA) for the projection; 4, 5, 6: error-free int8 digit
                                   products on tcgen05/TMEM with 7+8(slices-1) bits per operand (needs zNcube % 16 == 0) */
+    int refine;                /* slices != 0 only: steps of iterative refinement of (A K A^T + Sigma)^-1 y against the fp64
+                                  matrix-free operator before the mean K A3^T alpha is formed (0 = none; 1 is the default
+                                  of the Python surface)                                                              */
 } gb_hyper;
 
 /* Builds the device-resident problem: computes both sensitivity matrices on the GPU

@@ -28,7 +28,7 @@ def test_int8_examples_vs_committed_vtk_goldens(ctx, which, prec):
     assert abs(inv.logl - float(f["logl"])) < 1e-3
 
 
-@pytest.mark.parametrize("shape,kf,nd", [((5, 3, 16), "exp", 3), ((9, 7, 16), "sparse", 4), ((6, 5, 32), "matern32", 5),
+@pytest.mark.parametrize("shape,kf,nd", [((5, 4, 16), "exp", 3), ((9, 8, 16), "sparse", 4), ((6, 5, 32), "matern32", 5),
                                          ((16, 16, 16), "exp", 50), ((11, 4, 48), "exp", 0)])
 @pytest.mark.parametrize("prec", ["int8x5", "int8x6"])
 def test_int8_cubing_vs_oracle(ctx, shape, kf, nd, prec):

@@ -32,14 +32,16 @@ def main():
         mu0, var0, logl0, info0 = prob.predict(h0)
         t0 = prob.timings()
         for S in (4, 5, 6):
-            h = prob.hyper(inv.gp_length, inv.gp_sigma, inv.coeffm, inv.gp_amp, kf, slices=S)
-            prob.predict(h)
-            mu, var, logl, info = prob.predict(h)
-            t = prob.timings()
-            emu = np.abs(mu - mu0).max() / np.abs(mu0).max()
-            evar = np.abs(var - var0).max() / np.abs(var0).max()
-            print("%s %-8s nd=%-3d S=%d  mean err %.2e  var err %.2e  dlogl %.2e  info=%d | project %.2f ms (fp64 %.2f ms)  total %.2f (fp64 %.2f)"
-                  % (shape, kf, nd, S, emu, evar, abs(logl - logl0), info, t["project"], t0["project"], t["total"], t0["total"]), flush=True)
+            for nref in (0, 1, 2):
+                h = prob.hyper(inv.gp_length, inv.gp_sigma, inv.coeffm, inv.gp_amp, kf, slices=S, refine=nref)
+                prob.predict(h)
+                mu, var, logl, info = prob.predict(h)
+                t = prob.timings()
+                emu = np.abs(mu - mu0).max() / np.abs(mu0).max()
+                evar = np.abs(var - var0).max() / np.abs(var0).max()
+                print("%s %-8s nd=%-3d S=%d refine=%d  mean err %.2e  var err %.2e  dlogl %.2e  info=%d | project %.2f ms (fp64 %.2f)  aka %.2f chol %.2f trsm %.2f (fp64 %.2f)  total %.2f (fp64 %.2f)"
+                      % (shape, kf, nd, S, nref, emu, evar, abs(logl - logl0), info, t["project"], t0["project"], t["aka"], t["chol"], t["trsm"], t0["trsm"],
+                         t["total"], t0["total"]), flush=True)
 
 
 if __name__ == "__main__":
