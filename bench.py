@@ -12,7 +12,8 @@ projection A.K.A^T + Cholesky + triangular solves + posterior mean + variance di
   e2e       the same metric through the public Python API, ``Inversion.cubing(...)`` with HOST NumPy arrays:
             includes building the device problem (sensitivity matrices on the GPU), every H2D copy and the D2H
             of the six result cubes.
-  roofline  the dominant kernel (fused covariance assembly + projection on the fp64 DMMA tensor pipe).
+  roofline  the dominant kernel: fused covariance generation + projection Pt = A.K, by default exact int8 digit
+            products on the tcgen05 tensor cores (--precision int8x5), or the fp64 DMMA tensor pipe (--precision fp64).
   cpu_baseline  the oracle's lean NumPy/SciPy restatement of the reference on this box's host cores (bounded sample).
 
 For N > 1 (torchrun) the voxel columns of Pt = A.K are sharded over ranks; the only data-path collective
@@ -38,16 +39,16 @@ WORKLOADS = {
     "cfg1b": dict(shape=(16, 16, 16), kernel="exp", nd=50, name="16x16x16 cube (exp, nd=50)"),
     "cfg2": dict(shape=(32, 32, 32), kernel="exp", nd=0, name="32x32x32 cube, grav+mag joint inversion, sqexp kernel, fp64"),
     "cfg3": dict(shape=(64, 64, 32), kernel="matern32", nd=50, gl_mult=(1.0, 1.01, 1.02),
-                 name="64x64x32 cube, grav+mag + 50 drill constraints, Matern-3/2 cross-cov (fp64 path)"),
-    "cfg3e": dict(shape=(64, 64, 32), kernel="exp", nd=0, name="64x64x32 two-property cube, sqexp (fp64 path)"),
-    "cfg4": dict(shape=(96, 96, 48), kernel="exp", nd=0, name="96x96x48 cube, 2-property joint inversion (fp64 path)"),
+                 name="64x64x32 cube, grav+mag + 50 drill constraints, Matern-3/2 cross-cov"),
+    "cfg3e": dict(shape=(64, 64, 32), kernel="exp", nd=0, name="64x64x32 two-property cube, sqexp"),
+    "cfg4": dict(shape=(96, 96, 48), kernel="exp", nd=0, name="96x96x48 cube, 2-property joint inversion"),
 }
 METRIC = "voxels/sec joint-inversion (cov+chol+solve)"
 
 
 def read_peaks():
     peaks = {}
-    for name in ("MEASURED_PEAKS.json", os.path.join("profiles", "fp64_peaks_r1.json")):
+    for name in ("MEASURED_PEAKS.json", os.path.join("profiles", "fp64_peaks_r1.json"), os.path.join("profiles", "int8_peaks_r1.json")):
         p = os.path.join(ROOT, name)
         if os.path.exists(p):
             try:
@@ -124,7 +125,7 @@ def run_ours(args):
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     xN, yN, zN = wl["shape"]
-    cfg = synth.settings(xN, yN, zN, kernelfunc=wl["kernel"], precision=args.precision)
+    cfg = synth.settings(xN, yN, zN, kernelfunc=wl["kernel"], precision=args.precision, refine=args.refine)
     config_loader.load_settings(cfg, make_outpath=False)
     slices = inversion.Inversion._slices()
     N, Ns, nd = xN * yN * zN, xN * yN, wl["nd"]
@@ -144,7 +145,7 @@ def run_ours(args):
     y = np.hstack([(f["grav"] - f["grav"].mean()) / f["grav"].std(), (f["mag"] - f["mag"].mean()) / f["mag"].std(),
                    (f["drillfield"] - f["drillfield"].mean()) / f["drillfield"].std() if nd else np.zeros(0)])
     prob.set_data(y)
-    h = prob.hyper(gl_eff, config_loader.gp_err, config_loader.gp_coeff, 1.0, wl["kernel"], slices=slices)
+    h = prob.hyper(gl_eff, config_loader.gp_err, config_loader.gp_coeff, 1.0, wl["kernel"], slices=slices, refine=args.refine)
     t_sens_ms = prob.timings()["a_sens"]
     for _ in range(args.warmup):
         prob.predict(h, want_host=False)
@@ -200,21 +201,43 @@ def run_ours(args):
     fl = algorithmic_flops(N, Ns, nd, c1 - c0)
     proj_s = stage_ms["project"] / 1e3
     achieved = fl["project"] / proj_s / 1e12
-    fp64_peak = peaks.get("cublas_dgemm_8192_tflops")
-    roofline = {"kernel": "gemm_f64_kernel<B_GEN> (fused covariance assembly + projection Pt = A.K, fp64 DMMA)",
-                "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": (achieved / fp64_peak) if fp64_peak else None,
-                "peak_source": "fp64 tensor pipe measured on this pool with tools/peaks.cu (cuBLAS DGEMM 8192^3; DMMA issue peak %s); "
-                               "MEASURED_PEAKS.json carries no fp64 figure (its bf16 figure, %s TFLOP/s, does not bound an fp64 kernel)"
-                               % (peaks.get("dmma_tflops_w16"), peaks.get("bf16_tflops")),
-                "algorithmic_flops_per_launch": fl["project"], "ms_per_launch": stage_ms["project"],
-                "share_of_step": stage_ms["project"] / ms_per_step,
-                "traffic": peaks.get("traffic_project_%s" % args.workload)}
+    if slices:
+        # int8 digit-slice kernel: every algorithmic fp64 multiply-add is S(S+1)/2 exact int8 digit products on the
+        # tensor cores; the ceiling is the measured dense int8 tcgen05 rate (tools/peaks_i8.cu) divided by that count.
+        nprod = slices * (slices + 1) // 2
+        runs = [r for r in peaks.get("runs", []) if r.get("unrolled") and r.get("n", 0) >= 128]
+        i8_peak = max([r["int8_tops"] for r in runs] + [0.0]) or None
+        peak = (i8_peak / nprod) if i8_peak else None
+        roofline = {"kernel": "ozaki_project_kernel<%d> (fused covariance-digit generation + projection Pt = A.K; tcgen05.mma kind::i8, "
+                              "%d balanced 8-bit digits per operand, exact int32 accumulation in TMEM)" % (slices, slices),
+                    "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s (fp64-equivalent, algorithmic flops counted once)",
+                    "frac": (achieved / peak) if peak else None,
+                    "int8_tops_achieved": achieved * nprod, "int8_tops_peak_measured": i8_peak, "digit_products_per_mac": nprod,
+                    "peak_source": "dense int8 tcgen05 rate measured on this pool with tools/peaks_i8.cu (profiles/int8_peaks_r1.json: 8192 MAC/clk/SM, "
+                                   "nominal 4.5 POP/s = 2x the bf16 figure of MEASURED_PEAKS.json, %s TFLOP/s burst), divided by the %d digit "
+                                   "products per multiply-add" % (peaks.get("bf16_tflops"), nprod),
+                    "algorithmic_flops_per_launch": fl["project"], "ms_per_launch": stage_ms["project"],
+                    "share_of_step": stage_ms["project"] / ms_per_step,
+                    "traffic": peaks.get("traffic_project_%s_int8x%d" % (args.workload, slices))}
+        dtype = "s8 digit slices x%d (exact s32 accumulate) for the three dense products + f64 Cholesky / refinement" % slices
+    else:
+        fp64_peak = peaks.get("cublas_dgemm_8192_tflops")
+        roofline = {"kernel": "gemm_f64_kernel<B_GEN> (fused covariance assembly + projection Pt = A.K, fp64 DMMA)",
+                    "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": (achieved / fp64_peak) if fp64_peak else None,
+                    "peak_source": "fp64 tensor pipe measured on this pool with tools/peaks.cu (cuBLAS DGEMM 8192^3; DMMA issue peak %s); "
+                                   "MEASURED_PEAKS.json carries no fp64 figure (its bf16 figure, %s TFLOP/s, does not bound an fp64 kernel)"
+                                   % (peaks.get("dmma_tflops_w16"), peaks.get("bf16_tflops")),
+                    "algorithmic_flops_per_launch": fl["project"], "ms_per_launch": stage_ms["project"],
+                    "share_of_step": stage_ms["project"] / ms_per_step,
+                    "traffic": peaks.get("traffic_project_%s" % args.workload)}
+        dtype = "f64"
     out = {"metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype,
            "data": "synthetic (cylinders truth cube, forward-simulated grav/mag surveys, seed 0)",
            "config": {"workload": wl["name"], "workload_id": args.workload, "voxels": N, "sensors_per_survey": Ns, "drill_rows": nd,
-                      "data_rows_M": M, "kernel": wl["kernel"], "parallelism": "voxel-column shards of Pt x%d" % world,
+                      "data_rows_M": M, "kernel": wl["kernel"], "precision": args.precision + (" + %d refinement step(s)" % args.refine if slices else ""),
+                      "parallelism": "voxel-column shards of Pt x%d" % world,
                       "l2": "inputs larger than L2 (A and Pt are %.1f GB)" % (prob.device_bytes() / 1e9),
                       "device_bytes": prob.device_bytes()},
            "wall_ms_per_step": wall_s * 1e3 / args.steps, "stage_ms": stage_ms, "a_sens_ms": t_sens_ms,
@@ -315,7 +338,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GEOBO_B200_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("GEOBO_B200_PRECISION", "fp64"),
+    ap.add_argument("--refine", type=int, default=1, help="refinement steps of the int8 paths (fp64 matrix-free residual)")
+    ap.add_argument("--precision", default=os.environ.get("GEOBO_B200_PRECISION", "int8x5"),
                     choices=["fp64", "int8x4", "int8x5", "int8x6"],
                     help="projection arithmetic: fp64 DMMA, or error-free int8 digit products on tcgen05 (31/39/47 bits)")
     ap.add_argument("--e2e-steps", type=int, default=5)

@@ -632,10 +632,13 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     w.linv = p->linv; w.logdet = p->scal; w.info = p->info;
     GB_CUDA(ctx, chol_factor(p->Bm, Mp, (int)Mp, (int)M, w, s));
     GB_CUDA(ctx, cudaEventRecord(p->ev[6], s));
-    GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->ysol, 16, 1, p->ytmp, s));
-    dot_self_kernel<<<1, 256, 0, s>>>(p->ysol, M, p->scal + 1);
-    GB_CUDA(ctx, cudaGetLastError());
     const bool int8_var = full && h->slices != 0 && Mp <= 16384;
+    if (!int8_var) {
+        GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->ysol, 16, 1, p->ytmp, s));
+        dot_self_kernel<<<1, 256, 0, s>>>(p->ysol, M, p->scal + 1);
+        GB_CUDA(ctx, cudaGetLastError());
+        p->nlaunch += 2 * (Mp / 128) + 1;
+    }
     if (int8_var) {
         // ---- variance and mean without ever forming V = L^-1 Pt (:114-117) in memory:
         //   Linv = L^-1 explicitly (fp64 blocked solve against the identity), alpha = Linv^T u,
@@ -646,7 +649,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
             if (p->l8) { cudaFree(p->l8); p->l8 = nullptr; }
             if (!p->Linv) {
                 GB_CUDA(ctx, cudaMalloc((void**)&p->Linv, (size_t)Mp * Mp * sizeof(double)));
-                GB_CUDA(ctx, cudaMalloc((void**)&p->tmpL, (size_t)128 * Mp * sizeof(double)));
+                GB_CUDA(ctx, cudaMalloc((void**)&p->tmpL, (size_t)Mp * Mp * sizeof(double)));
                 GB_CUDA(ctx, cudaMalloc((void**)&p->alpha, (size_t)Mp * sizeof(double)));
                 GB_CUDA(ctx, cudaMalloc((void**)&p->l_exp, (size_t)Mp * sizeof(int)));
                 GB_CUDA(ctx, cudaMalloc((void**)&p->partial, (size_t)(Mp / 128) * ldp * sizeof(double)));
@@ -655,18 +658,18 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
                 GB_CUDA(ctx, cudaMalloc((void**)&p->rf_part, (size_t)16 * p->Kp * sizeof(double)));
                 GB_CUDA(ctx, cudaMalloc((void**)&p->rf_t, (size_t)3 * Mp * sizeof(double)));
                 GB_CUDA(ctx, cudaMemsetAsync(p->rf_t, 0, (size_t)3 * Mp * sizeof(double), s));
-                p->bytes += (size_t)Mp * Mp * 8 + (size_t)128 * Mp * 8 + (size_t)(Mp / 128) * ldp * 8;
+                p->bytes += 2 * (size_t)Mp * Mp * 8 + (size_t)(Mp / 128) * ldp * 8;
             }
             GB_CUDA(ctx, cudaMalloc((void**)&p->l8, (size_t)ozaki_rows_bytes(Mp, Mp, S)));
             p->bytes += (size_t)ozaki_rows_bytes(Mp, Mp, S);
             p->var_slices = S;
         }
-        GB_CUDA(ctx, cudaMemsetAsync(p->Linv, 0, (size_t)Mp * Mp * sizeof(double), s));
-        set_identity_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(p->Linv, Mp);
-        GB_CUDA(ctx, cudaGetLastError());
-        GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->Linv, Mp, (int)Mp, p->tmpL, s, 1));
-        // alpha = L^-T u, then refined against the fp64 matrix-free operator (the factor came from digit-rounded operands)
-        GB_CUDA(ctx, refine_linv_t(p->Linv, Mp, p->ysol, 16, p->alpha, s));
+        GB_CUDA(ctx, chol_inverse(p->Bm, Mp, (int)Mp, w, p->Linv, p->tmpL, s, &p->nlaunch));
+        // u = Linv y (:105), u.u for logl, alpha = L^-T u -- then refined against the fp64 matrix-free operator
+        // (the factor came from digit-rounded operands)
+        double* rt0 = p->rf_t + 2 * Mp;
+        GB_CUDA(ctx, refine_apply_inverse(p->Linv, Mp, p->ydev, rt0, p->alpha, 0, s));
+        GB_CUDA(ctx, refine_dot(rt0, rt0, M, p->scal + 1, s));
         RefineArgs ra;
         ra.A[0] = p->A[0]; ra.A[1] = p->A[1]; ra.tables = p->tables; ra.drill = p->drill_dev; ra.partial = p->rf_part;
         ra.Ns = Ns; ra.N = p->N; ra.lda = p->lda; ra.Kp = p->Kp; ra.ext = p->ext; ra.C0 = p->C0; ra.nd = p->nd;
@@ -695,7 +698,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         GB_CUDA(ctx, ozaki_colsumsq_tri(p->l8, p->l_exp, p->b8, p->b_exp, (int)Mp, ldp, S, p->partial, ctx->sm_count, s));
         GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
         GB_CUDA(ctx, ozaki_var_finalize(p->partial, (int)(Mp / 128), ldp, ncp, ncol, h->gp_amp, p->var, s));
-        p->nlaunch += 2 * (Mp / 128) + 8;
+        p->nlaunch += 10;
     } else if (full) {
         // ---- V = L^-1 Pt (:114) in place, then mean (:115) and variance diagonal (:117)
         GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->Pt, ldp, (int)ldp, p->tmp, s));
@@ -727,7 +730,7 @@ static int collect_timings(gb_problem* p) {
         // Cholesky (potrf + panel + trailing per block), u solve (2 GEMMs per block), dot; the mean / variance
         // stage adds its own count (p->nlaunch) in run_predict
         const long nblk = p->Mp / 128;
-        p->ms[GB_T_LAUNCHES] = (double)(5 + (p->nd ? 2 : 0) + (3 * nblk - 2) + 2 * nblk + 1 + p->nlaunch);
+        p->ms[GB_T_LAUNCHES] = (double)(4 + (p->nd ? 2 : 0) + (3 * nblk - 2) + p->nlaunch);
     }
     return GB_OK;
 }

@@ -8,6 +8,9 @@
 // 128-row block of V is one wide GEMM against all previous rows, then a GEMM with the block inverse.
 #include "common.cuh"
 
+#include <algorithm>
+#include <utility>
+
 constexpr int NB = 128;
 constexpr int PLD = NB + 1;   // padded leading dimension in shared memory
 
@@ -198,4 +201,50 @@ cudaError_t chol_forward_solve(const double* L, long ldl, int Mp, const CholWork
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+// Linv diagonal blocks <- inverses of the 128 x 128 diagonal blocks of L (everything else zero)
+__global__ void linv_diag_init_kernel(const double* __restrict__ linv_blocks, double* __restrict__ Linv, long n) {
+    const int kb = blockIdx.x;
+    const double* src = linv_blocks + (long)kb * NB * NB;
+    double* dst = Linv + ((long)kb * NB) * n + (long)kb * NB;
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) dst[(long)(e >> 7) * n + (e & (NB - 1))] = src[e];
+}
+
+cudaError_t chol_inverse(const double* L, long ldl, int Mp, const CholWork& w, double* Linv, double* Ltmp, cudaStream_t s, long* nlaunch) {
+    cudaError_t e = cudaMemsetAsync(Linv, 0, (size_t)Mp * Mp * sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    const int nblk = Mp / NB;
+    linv_diag_init_kernel<<<nblk, 256, 0, s>>>(w.linv, Linv, Mp);
+    if (nlaunch) *nlaunch += 1;
+    // groups of already inverted diagonal blocks: (start row, rows); merged pairwise per level
+    std::vector<std::pair<int, int>> groups;
+    for (int kb = 0; kb < nblk; ++kb) groups.push_back({kb * NB, NB});
+    while (groups.size() > 1) {
+        std::vector<std::pair<int, int>> next;
+        std::vector<gemm::Task> t1, t2;
+        for (size_t g = 0; g + 1 < groups.size(); g += 2) {
+            const int r0 = groups[g].first, n0 = groups[g].second, r1 = groups[g + 1].first, n1 = groups[g + 1].second;
+            double* T = Ltmp + (long)r1 * Mp + r0;
+            // T = L21 . X11          (B given as [K][N])
+            t1.push_back(make_task(L + (long)r1 * ldl + r0, ldl, Linv + (long)r0 * Mp + r0, Mp, nullptr, 0, T, Mp, n1, n0, n0, 1.0, 0.0, 0));
+            // X21 = - X22 . T
+            t2.push_back(make_task(Linv + (long)r1 * Mp + r1, Mp, T, Mp, nullptr, 0, Linv + (long)r1 * Mp + r0, Mp, n1, n0, n1, -1.0, 0.0, 0));
+            next.push_back({r0, n0 + n1});
+        }
+        if (groups.size() & 1) next.push_back(groups.back());
+        for (int pass = 0; pass < 2; ++pass) {
+            const std::vector<gemm::Task>& tt = pass ? t2 : t1;
+            for (size_t i = 0; i < tt.size(); i += gemm::MAX_TASKS) {
+                gemm::TaskBatch b;
+                b.n = (int)std::min<size_t>(gemm::MAX_TASKS, tt.size() - i);
+                for (int k = 0; k < b.n; ++k) b.t[k] = tt[i + k];
+                e = gemm::launch(b, gemm::B_N, s);
+                if (e != cudaSuccess) return e;
+                if (nlaunch) *nlaunch += 1;
+            }
+        }
+        groups.swap(next);
+    }
+    return cudaGetLastError();
 }

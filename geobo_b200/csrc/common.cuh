@@ -87,7 +87,7 @@ struct Task {
     const int* Lrow;      // B_GEN: extended-lattice id of output column n  (Lrow[n])
     const int* Lcol;      // B_GEN: extended-lattice id of contraction index k (Lcol[k])
 };
-constexpr int MAX_TASKS = 6;
+constexpr int MAX_TASKS = 32;
 struct TaskBatch {
     Task t[MAX_TASKS];
     int n;
@@ -177,6 +177,10 @@ struct CholWork {
 };
 cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, cudaStream_t s);
 // V = L^-1 Pt in place (Pt: [Mp][ldp]); tmp: [128][ldp]
+// Linv = L^-1 (lower triangular, Mp x Mp, ld = Mp) by recursive doubling from the 128 x 128 diagonal-block inverses that
+// chol_factor left in w.linv: [L11 0; L21 L22]^-1 = [X11 0; -X22 L21 X11, X22]; two batched GEMM launches per level.
+// Ltmp: Mp x Mp scratch.
+cudaError_t chol_inverse(const double* L, long ldl, int Mp, const CholWork& w, double* Linv, double* Ltmp, cudaStream_t s, long* nlaunch);
 // tri != 0: the right-hand side is lower triangular (e.g. the identity): block row kb only has columns < 128 (kb + 1)
 cudaError_t chol_forward_solve(const double* L, long ldl, int Mp, const CholWork& w, double* Pt, long ldp, int ncols,
                                double* tmp, cudaStream_t s, int tri = 0);

@@ -55,11 +55,11 @@ extern "C" {
 #define GB_T_TABLES 1      /* stationary covariance tables        */
 #define GB_T_PROJECT 2     /* Pt = A . K  (fused assembly + GEMM) */
 #define GB_T_DRILLROWS 3   /* drill rows of Pt / AkA gathers      */
-#define GB_T_AKA 4         /* AkA = A . Pt^T + Sigma              */
+#define GB_T_AKA 4         /* AkA = A . Pt^T + Sigma (int8 paths: incl. slicing Pt rows) */
 #define GB_T_ALLREDUCE 5   /* NCCL all-reduce of AkA (multi-GPU)  */
 #define GB_T_CHOL 6        /* Cholesky of AkA                     */
-#define GB_T_TRSM 7        /* V = L^-1 Pt, u = L^-1 y             */
-#define GB_T_MEANVAR 8     /* mean, variance diag, logl           */
+#define GB_T_TRSM 7        /* u = L^-1 y; fp64: V = L^-1 Pt; int8: Linv, refinement of alpha, mean, colsumsq(Linv.Pt) */
+#define GB_T_MEANVAR 8     /* fp64: mean + variance diag from V; int8: variance finalisation */
 #define GB_T_TOTAL 9       /* whole gb_predict on device          */
 #define GB_T_D2H 10        /* result copies to host               */
 #define GB_T_LAUNCHES 11   /* number of library kernels launched by the last gb_predict / gb_neg_logl (a count, not ms) */

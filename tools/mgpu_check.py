@@ -15,8 +15,10 @@ def main():
     ctx = _lib.default_context()
     rank, world = dist.init_from_env(ctx)
     worst = 0.0
-    for shape, kf, nd in [((16, 16, 8), "exp", 5), ((12, 10, 9), "sparse", 0), ((16, 12, 6), "matern32", 7)]:
-        cfg = synth.settings(*shape, kernelfunc=kf)
+    cases = [((16, 16, 8), "exp", 5, "fp64"), ((12, 10, 9), "sparse", 0, "fp64"), ((16, 12, 6), "matern32", 7, "fp64"),
+             ((16, 16, 16), "exp", 9, "int8x5"), ((12, 11, 32), "matern32", 6, "int8x6"), ((20, 16, 16), "sparse", 0, "int8x5")]
+    for shape, kf, nd, prec in cases:
+        cfg = synth.settings(*shape, kernelfunc=kf, precision=prec)
         config_loader.load_settings(cfg, make_outpath=False)
         f = synth.make_inputs(nd=nd, seed=1, ctx=ctx)
         inv = inversion.Inversion()
@@ -35,7 +37,7 @@ def main():
                     assert np.isnan(a).all()
                     continue
                 worst = max(worst, float(np.abs(a - r).max() / np.abs(r).max()))
-            assert abs(inv.logl - ex["logl"]) < 1e-7 * abs(ex["logl"]), (inv.logl, ex["logl"])
+            assert abs(inv.logl - ex["logl"]) < (1e-7 if prec == "fp64" else 1e-5) * abs(ex["logl"]), (inv.logl, ex["logl"])
         dist.barrier()
     if rank == 0:
         assert worst < 1e-7, worst
