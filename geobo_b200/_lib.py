@@ -43,6 +43,7 @@ _SIGNATURES = {
     "gb_version": (C.c_int, []),
     "gb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "gb_ctx_destroy": (C.c_int, [_P]),
+    "gb_ctx_release_cache": (C.c_int, [_P]),
     "gb_last_error": (C.c_char_p, [_P]),
     "gb_device_info": (C.c_int, [_P, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -118,6 +119,10 @@ class Context:
         if getattr(self, "h", None):
             self.lib.gb_ctx_destroy(self.h)
             self.h = None
+
+    def release_cache(self):
+        """Return the cached device / pinned-host buffers of closed problems to the driver."""
+        self.check(self.lib.gb_ctx_release_cache(self.h))
 
     def device_info(self):
         name = C.create_string_buffer(256)

@@ -41,9 +41,73 @@ extern "C" int gb_ctx_create(int device, gb_ctx** out) {
     return GB_OK;
 }
 
+// ---------------------------------------------------------------------------------- cached allocators
+static void release_cache(gb_ctx* ctx) {
+    for (auto& kv : ctx->dev_cache) { cudaFree(kv.second); ctx->dev_sizes.erase(kv.second); }
+    ctx->dev_cache.clear();
+    for (auto& kv : ctx->host_cache) { cudaFreeHost(kv.second); ctx->host_sizes.erase(kv.second); }
+    ctx->host_cache.clear();
+}
+
+cudaError_t gb_dev_malloc(gb_ctx* ctx, void** p, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    auto it = ctx->dev_cache.find(bytes);
+    if (it != ctx->dev_cache.end()) {
+        *p = it->second;
+        ctx->dev_cache.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {      // make room: drop everything cached, retry once
+        cudaGetLastError();
+        release_cache(ctx);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) ctx->dev_sizes[*p] = bytes;
+    return e;
+}
+
+void gb_dev_free(gb_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->dev_sizes.find(p);
+    if (it == ctx->dev_sizes.end()) { cudaFree(p); return; }
+    ctx->dev_cache.insert({it->second, p});
+}
+
+cudaError_t gb_host_malloc(gb_ctx* ctx, void** p, size_t bytes) {
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    auto it = ctx->host_cache.find(bytes);
+    if (it != ctx->host_cache.end()) {
+        *p = it->second;
+        ctx->host_cache.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMallocHost(p, bytes);
+    if (e == cudaSuccess) ctx->host_sizes[*p] = bytes;
+    return e;
+}
+
+void gb_host_free(gb_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->host_sizes.find(p);
+    if (it == ctx->host_sizes.end()) { cudaFreeHost(p); return; }
+    ctx->host_cache.insert({it->second, p});
+}
+
+extern "C" int gb_ctx_release_cache(gb_ctx* ctx) {
+    if (!ctx) return GB_ERR_ARG;
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    release_cache(ctx);
+    return GB_OK;
+}
+
 extern "C" int gb_ctx_destroy(gb_ctx* ctx) {
     if (!ctx) return GB_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    release_cache(ctx);
     comm_destroy(ctx);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -281,7 +345,7 @@ struct gb_problem {
 
 template <typename T>
 static cudaError_t dev_alloc(gb_problem* p, T** ptr, size_t count, bool zero) {
-    cudaError_t e = cudaMalloc((void**)ptr, count * sizeof(T));
+    cudaError_t e = gb_dev_malloc(p->ctx, (void**)ptr, count * sizeof(T));
     if (e != cudaSuccess) return e;
     p->bytes += count * sizeof(T);
     if (zero) e = cudaMemsetAsync(*ptr, 0, count * sizeof(T), p->ctx->stream);
@@ -298,9 +362,9 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
                     p->rf_w, p->rf_z, p->rf_part, p->rf_t,
                     p->linv, p->scal, p->info, p->mu, p->var};
     for (void* q : ptrs)
-        if (q) cudaFree(q);
-    if (p->y_host_pinned) cudaFreeHost(p->y_host_pinned);
-    if (p->out_pinned) cudaFreeHost(p->out_pinned);
+        if (q) gb_dev_free(p->ctx, q);
+    gb_host_free(p->ctx, p->y_host_pinned);
+    gb_host_free(p->ctx, p->out_pinned);
     if (p->ev_ok)
         for (auto& e : p->ev) cudaEventDestroy(e);
     delete p;
@@ -370,8 +434,8 @@ extern "C" int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* d, gb_probl
     PCUDA(dev_alloc(p, &p->info, 4, true));
     PCUDA(dev_alloc(p, &p->mu, (size_t)3 * p->ncol, true));
     PCUDA(dev_alloc(p, &p->var, (size_t)3 * p->ncol, true));
-    PCUDA(cudaMallocHost((void**)&p->y_host_pinned, (size_t)p->Mp * sizeof(double)));
-    PCUDA(cudaMallocHost((void**)&p->out_pinned, (size_t)(6 * p->ncol + 8) * sizeof(double)));
+    PCUDA(gb_host_malloc(ctx, (void**)&p->y_host_pinned, (size_t)p->Mp * sizeof(double)));
+    PCUDA(gb_host_malloc(ctx, (void**)&p->out_pinned, (size_t)(6 * p->ncol + 8) * sizeof(double)));
     if (p->nd) PCUDA(cudaMemcpyAsync(p->drill_dev, p->drill.data(), p->nd * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     PCUDA(launch_lattice_ids(p->n, p->L, p->Kp, ctx->stream));
 
@@ -538,23 +602,23 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
                            "(got zNcube=%lld, columns=%ld); use slices = 0", (long long)p->n[2], ncol);
         if (p->a8_slices != S) {   // digit planes of the sensitivities: built once per problem and slice count
             for (int c = 0; c < 2; ++c) {
-                if (p->a8[c]) { cudaFree(p->a8[c]); p->a8[c] = nullptr; }
-                GB_CUDA(ctx, cudaMalloc((void**)&p->a8[c], (size_t)ozaki_rows_bytes(Ns, p->Kp, S)));
-                if (!p->a_exp[c]) GB_CUDA(ctx, cudaMalloc((void**)&p->a_exp[c], (size_t)Ns * sizeof(int)));
+                if (p->a8[c]) { gb_dev_free(ctx, p->a8[c]); p->a8[c] = nullptr; }
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a8[c], (size_t)ozaki_rows_bytes(Ns, p->Kp, S)));
+                if (!p->a_exp[c]) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a_exp[c], (size_t)Ns * sizeof(int)));
                 GB_CUDA(ctx, ozaki_slice_sens(p->A[c], Ns, p->N, p->lda, S, p->a_exp[c], p->a8[c], p->Kp, s));
             }
-            if (p->t8) { cudaFree(p->t8); p->t8 = nullptr; }
-            GB_CUDA(ctx, cudaMalloc((void**)&p->t8, (size_t)ozaki_table_bytes(p->ext, S)));
-            if (!p->t_exp) GB_CUDA(ctx, cudaMalloc((void**)&p->t_exp, 16 * sizeof(int)));
+            if (p->t8) { gb_dev_free(ctx, p->t8); p->t8 = nullptr; }
+            GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->t8, (size_t)ozaki_table_bytes(p->ext, S)));
+            if (!p->t_exp) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->t_exp, 16 * sizeof(int)));
             // digit scratch shared by the AkA products (row digits of three Pt blocks) and the variance product
             // (transposed digits of all of Pt): the two uses are sequential
-            if (p->b8) { cudaFree(p->b8); p->b8 = nullptr; }
-            if (p->b_exp) { cudaFree(p->b_exp); p->b_exp = nullptr; }
+            if (p->b8) { gb_dev_free(ctx, p->b8); p->b8 = nullptr; }
+            if (p->b_exp) { gb_dev_free(ctx, p->b_exp); p->b_exp = nullptr; }
             const size_t aka_bytes = 3 * (size_t)ozaki_rows_bytes(Ns, ncp, S, ozaki_tile_n(S));
             const size_t var_bytes = (size_t)ozaki_cols_bytes(ldp, Mp, S);
             p->b8_bytes = aka_bytes > var_bytes ? aka_bytes : var_bytes;
-            GB_CUDA(ctx, cudaMalloc((void**)&p->b8, p->b8_bytes));
-            GB_CUDA(ctx, cudaMalloc((void**)&p->b_exp, (size_t)(ldp > 3 * Ns ? ldp : 3 * Ns) * sizeof(int)));
+            GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->b8, p->b8_bytes));
+            GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->b_exp, (size_t)(ldp > 3 * Ns ? ldp : 3 * Ns) * sizeof(int)));
             p->bytes += 2 * (size_t)ozaki_rows_bytes(Ns, p->Kp, S) + p->b8_bytes;
             p->a8_slices = S;
         }
@@ -646,21 +710,21 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         //   colsumsq(Linv . Pt) on the int8 tensor cores with the reduction in the epilogue (:117, diag only).
         const int S = h->slices;
         if (p->var_slices != S) {
-            if (p->l8) { cudaFree(p->l8); p->l8 = nullptr; }
+            if (p->l8) { gb_dev_free(ctx, p->l8); p->l8 = nullptr; }
             if (!p->Linv) {
-                GB_CUDA(ctx, cudaMalloc((void**)&p->Linv, (size_t)Mp * Mp * sizeof(double)));
-                GB_CUDA(ctx, cudaMalloc((void**)&p->tmpL, (size_t)Mp * Mp * sizeof(double)));
-                GB_CUDA(ctx, cudaMalloc((void**)&p->alpha, (size_t)Mp * sizeof(double)));
-                GB_CUDA(ctx, cudaMalloc((void**)&p->l_exp, (size_t)Mp * sizeof(int)));
-                GB_CUDA(ctx, cudaMalloc((void**)&p->partial, (size_t)(Mp / 128) * ldp * sizeof(double)));
-                GB_CUDA(ctx, cudaMalloc((void**)&p->rf_w, (size_t)3 * p->Kp * sizeof(double)));
-                GB_CUDA(ctx, cudaMalloc((void**)&p->rf_z, (size_t)3 * ncp * sizeof(double)));
-                GB_CUDA(ctx, cudaMalloc((void**)&p->rf_part, (size_t)16 * p->Kp * sizeof(double)));
-                GB_CUDA(ctx, cudaMalloc((void**)&p->rf_t, (size_t)3 * Mp * sizeof(double)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->Linv, (size_t)Mp * Mp * sizeof(double)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->tmpL, (size_t)Mp * Mp * sizeof(double)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->alpha, (size_t)Mp * sizeof(double)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->l_exp, (size_t)Mp * sizeof(int)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->partial, (size_t)(Mp / 128) * ldp * sizeof(double)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_w, (size_t)3 * p->Kp * sizeof(double)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_z, (size_t)3 * ncp * sizeof(double)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_part, (size_t)16 * p->Kp * sizeof(double)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_t, (size_t)3 * Mp * sizeof(double)));
                 GB_CUDA(ctx, cudaMemsetAsync(p->rf_t, 0, (size_t)3 * Mp * sizeof(double), s));
                 p->bytes += 2 * (size_t)Mp * Mp * 8 + (size_t)(Mp / 128) * ldp * 8;
             }
-            GB_CUDA(ctx, cudaMalloc((void**)&p->l8, (size_t)ozaki_rows_bytes(Mp, Mp, S)));
+            GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->l8, (size_t)ozaki_rows_bytes(Mp, Mp, S)));
             p->bytes += (size_t)ozaki_rows_bytes(Mp, Mp, S);
             p->var_slices = S;
         }

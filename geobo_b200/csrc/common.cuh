@@ -6,7 +6,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/geobo_b200.h"
@@ -19,7 +21,17 @@ struct gb_ctx {
     // NCCL (resolved lazily with dlopen, see comm.cu)
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    // size-keyed cache of device / pinned-host buffers released by destroyed problems: repeated Inversion.cubing()
+    // calls on the same cube reuse them instead of paying cudaMalloc / cudaFree of several GB per call
+    std::multimap<size_t, void*> dev_cache, host_cache;
+    std::unordered_map<void*, size_t> dev_sizes, host_sizes;
 };
+
+// cached allocators (api.cu); the cache is emptied on allocation failure and by gb_ctx_release_cache / gb_ctx_destroy
+cudaError_t gb_dev_malloc(gb_ctx* ctx, void** p, size_t bytes);
+void gb_dev_free(gb_ctx* ctx, void* p);
+cudaError_t gb_host_malloc(gb_ctx* ctx, void** p, size_t bytes);
+void gb_host_free(gb_ctx* ctx, void* p);
 
 extern std::string g_gb_create_error;
 

@@ -72,6 +72,10 @@ int gb_version(void);
 /* device < 0: use the current device. */
 int gb_ctx_create(int device, gb_ctx** out);
 int gb_ctx_destroy(gb_ctx* ctx);
+/* Device and pinned-host buffers of destroyed problems are kept in a size-keyed cache on the context so that repeated
+ * Inversion.cubing() calls on the same cube do not pay cudaMalloc/cudaFree of several GB each; this returns them to the
+ * driver (also done automatically when an allocation fails and by gb_ctx_destroy). */
+int gb_ctx_release_cache(gb_ctx* ctx);
 /* last error text of this context (ctx == NULL: of the last failed gb_ctx_create). */
 const char* gb_last_error(const gb_ctx* ctx);
 int gb_device_info(gb_ctx* ctx, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor,
