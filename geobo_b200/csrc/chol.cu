@@ -14,53 +14,127 @@
 constexpr int NB = 128;
 constexpr int PLD = NB + 1;   // padded leading dimension in shared memory
 
-// Factor one 128x128 diagonal block in place (lower), write its inverse to linv (row-major, upper zero).
-//
-// Register-tiled right-looking Cholesky: 256 threads as a 16 x 16 grid, thread (ty, tx) owns the 8 x 8
-// cyclic sub-matrix {(ty + 16a, tx + 16b)} of the (symmetric) block in registers; per pivot k the owner
-// publishes sqrt(d), the owners of column k publish the scaled column through shared memory, and every
-// thread applies the rank-1 update to its registers (2 barriers per pivot, no shared-memory matrix traffic).
-// The inverse of the factor (used for the panel solve and the blocked forward substitution) is then
-// built column by column with two lanes per column.
+// ---- potrf128 v2 ---------------------------------------------------------------------------------------------
+// Latency-optimised one-CTA Cholesky of a 128 x 128 diagonal block + its inverse.
+//  * factor: right-looking, register tiled (256 threads as 16 x 16, thread (ty, tx) owns the cyclic elements
+//    (ty + 16 a, tx + 16 b), LOWER triangle only); every thread also tracks the running diagonal of its 8 columns, so
+//    the 16 owners of pivot column k compute rsqrt(d_k) locally and ONE barrier per pivot suffices (the scaled column
+//    goes through a double-buffered shared array);
+//  * inverse: 16 x 16 diagonal blocks by one warp each (forward substitution in registers), then recursive doubling
+//    X21 = -X22 (L21 X11) for block sizes 16, 32, 64 with register-tiled shared-memory products.
+template <int SZ, int TI, int TJ>
+__device__ __forceinline__ void inv_level(double* __restrict__ S, double* __restrict__ T, int tid) {
+    // pairs of SZ x SZ diagonal blocks: (o, o + SZ), o = 2 SZ p.  X (strict lower) is stored transposed in the upper triangle
+    // of S: X[r][c] at S[c * PLD + r]; the diagonal of X is in xd (passed through T + 64*64).
+    constexpr int NPAIR = NB / (2 * SZ);
+    constexpr int TPP = 256 / NPAIR;                 // threads per pair
+    constexpr int GI = SZ / TI, GJ = SZ / TJ;        // tile grid
+    static_assert(GI * GJ == TPP, "tile grid must match the threads of a pair");
+    const double* xd = T + 64 * 64;
+    const int p = tid / TPP, t = tid % TPP, ti = (t / GJ) * TI, tj = (t % GJ) * TJ;
+    const int o1 = 2 * SZ * p, o2 = o1 + SZ;
+    double* Tp = T + p * SZ * SZ;
+    // T = L21 . X11   (X11 lower triangular incl. diagonal): T[i][j] = sum_{k >= j} L21[i][k] X11[k][j]
+    {
+        double acc[TI][TJ];
+#pragma unroll
+        for (int i = 0; i < TI; ++i)
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) acc[i][j] = 0.0;
+        for (int k = tj; k < SZ; ++k) {
+            double l[TI], x[TJ];
+#pragma unroll
+            for (int i = 0; i < TI; ++i) l[i] = S[(o2 + ti + i) * PLD + o1 + k];
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) {
+                const int c = tj + j;
+                x[j] = (k > c) ? S[(o1 + c) * PLD + o1 + k] : (k == c ? xd[o1 + c] : 0.0);
+            }
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) acc[i][j] = fma(l[i], x[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < TI; ++i)
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) Tp[(ti + i) * SZ + tj + j] = acc[i][j];
+    }
+    __syncthreads();
+    // X21 = - X22 . T   (X22 lower triangular): X21[i][j] = - sum_{k <= i} X22[i][k] T[k][j]
+    {
+        double acc[TI][TJ];
+#pragma unroll
+        for (int i = 0; i < TI; ++i)
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) acc[i][j] = 0.0;
+        for (int k = 0; k < ti + TI; ++k) {
+            double x[TI], tt[TJ];
+#pragma unroll
+            for (int i = 0; i < TI; ++i) {
+                const int r = ti + i;
+                x[i] = (k < r) ? S[(o2 + k) * PLD + o2 + r] : (k == r ? xd[o2 + r] : 0.0);
+            }
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) tt[j] = Tp[k * SZ + tj + j];
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) acc[i][j] = fma(x[i], tt[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < TI; ++i)
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) S[(o1 + tj + j) * PLD + o2 + ti + i] = -acc[i][j];
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256, 1) potrf128_kernel(double* __restrict__ Bm, long ldb, int k0, int Mtrue,
                                                           double* __restrict__ linv, double* __restrict__ logdet,
                                                           int* __restrict__ info) {
-    extern __shared__ double S[];   // [NB][PLD]; lower = L, strict upper = X^T (inverse)
-    __shared__ double colk[NB];
-    __shared__ double xd[NB];
+    extern __shared__ double S[];           // [NB][PLD]: lower = L, strict upper = X^T; then T [64*64] + xd [NB]
+    double* T = S + NB * PLD;
+    double* xd = T + 64 * 64;
+    __shared__ double colk[2][NB];
+    __shared__ double dsave[NB];
     __shared__ double red[NB];
-    __shared__ double pivs;
     __shared__ int bad;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     double* blk = Bm + (long)k0 * ldb + k0;
-    double reg[8][8];
+    double reg[8][8];                       // only b <= a is used (lower triangle of the cyclic tiling)
+    double dd[8];                           // running diagonal of columns tx + 16 b
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
+        for (int b = 0; b <= a; ++b) {
             const int r = ty + 16 * a, c = tx + 16 * b;
-            reg[a][b] = (c <= r) ? blk[(long)r * ldb + c] : blk[(long)c * ldb + r];   // only the lower triangle is valid in memory
+            reg[a][b] = (c <= r) ? blk[(long)r * ldb + c] : 0.0;
         }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { const int c = tx + 16 * b; dd[b] = blk[(long)c * ldb + c]; }
     if (tid == 0) bad = 0;
-    __syncthreads();
 #pragma unroll
     for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll 1
         for (int kk = 0; kk < 16; ++kk) {
             const int k = kb * 16 + kk;
-            if (ty == kk && tx == kk) {
-                const double d = reg[kb][kb];
-                if (!(d > 0.0) && bad == 0) bad = k0 + k + 1;
-                pivs = sqrt(d);
-            }
-            __syncthreads();
-            const double piv = pivs;
+            double* ck = colk[k & 1];
             if (tx == kk) {
+                const double d = dd[kb];
+                const double rs = rsqrt(d);
+                if (ty == kk) {
+                    if (!(d > 0.0) && bad == 0) bad = k0 + k + 1;
+                    dsave[k] = d;
+                    xd[k] = rs;                                  // 1 / L_kk = X_kk
+                    ck[k] = d * rs;                              // L_kk
+                }
 #pragma unroll
-                for (int a = 0; a < 8; ++a) {
+                for (int a = kb; a < 8; ++a) {
                     const int r = ty + 16 * a;
-                    if (r >= k) {
-                        const double l = (r == k) ? piv : reg[a][kb] / piv;
-                        colk[r] = l;
+                    if (r > k) {
+                        const double l = reg[a][kb] * rs;
+                        ck[r] = l;
                         reg[a][kb] = l;
                     }
                 }
@@ -68,62 +142,70 @@ __global__ void __launch_bounds__(256, 1) potrf128_kernel(double* __restrict__ B
             __syncthreads();
             double lr[8], lc[8];
 #pragma unroll
-            for (int a = 0; a < 8; ++a) lr[a] = colk[ty + 16 * a];
+            for (int a = kb; a < 8; ++a) lr[a] = ck[ty + 16 * a];
 #pragma unroll
-            for (int b = 0; b < 8; ++b) lc[b] = colk[tx + 16 * b];
+            for (int b = kb; b < 8; ++b) lc[b] = ck[tx + 16 * b];
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int b = kb; b < 8; ++b)
+                if (tx + 16 * b > k) dd[b] = fma(-lc[b], lc[b], dd[b]);
 #pragma unroll
-                for (int b = 0; b < 8; ++b)
-                    if (ty + 16 * a > k && tx + 16 * b > k) reg[a][b] -= lr[a] * lc[b];
+            for (int a = kb; a < 8; ++a)
+#pragma unroll
+                for (int b = kb; b <= a; ++b)
+                    if (ty + 16 * a > k && tx + 16 * b > k) reg[a][b] = fma(-lr[a], lc[b], reg[a][b]);
         }
     }
-    // publish L (lower) to shared memory and to the matrix
+    __syncthreads();
+    // publish L (lower incl. diagonal) to shared memory and to the matrix
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
+        for (int b = 0; b <= a; ++b) {
             const int r = ty + 16 * a, c = tx + 16 * b;
-            if (c <= r) {
+            if (c < r) {
                 S[r * PLD + c] = reg[a][b];
                 blk[(long)r * ldb + c] = reg[a][b];
             }
         }
+    if (tid < NB) {
+        const double l = dsave[tid] * xd[tid];
+        S[tid * PLD + tid] = l;
+        blk[(long)tid * ldb + tid] = l;
+        red[tid] = (k0 + tid < Mtrue) ? log(dsave[tid]) : 0.0;   // inversion.py:108: log(diag(L)**2) = log(d_k)
+    }
     __syncthreads();
-    // X = L^-1, column c by the lane pair (2c, 2c+1); X^T goes to the strict upper triangle of S
+    // ---- inverse, level 0: the eight 16 x 16 diagonal blocks, one warp each, lane j < 16 owns column j
     {
-        const int c = tid >> 1, h = tid & 1;
-        const int cmin = (tid & ~31) >> 1;          // smallest column handled by this warp: uniform loop bounds
-        const double xc = 1.0 / S[c * PLD + c];
-        if (h == 0) xd[c] = xc;
-        for (int r = cmin + 1; r < NB; ++r) {
-            double s0 = 0.0, s1 = 0.0;
-            if (r > c) {
-                int k = c + h;
-                if (k == c && k < r) { s0 = S[r * PLD + c] * xc; k += 2; }
-                for (; k + 2 < r; k += 4) {
-                    s0 = fma(S[r * PLD + k], S[c * PLD + k], s0);
-                    s1 = fma(S[r * PLD + k + 2], S[c * PLD + k + 2], s1);
+        const int w = tid >> 5, lane = tid & 31, o = 16 * w;
+        if (lane < 16) {
+            double x[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (i == lane) x[i] = xd[o + i];
+                else if (i > lane) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int kq = 0; kq < 16; ++kq)
+                        if (kq < i) s = fma(S[(o + i) * PLD + o + kq], x[kq], s);     // x[kq] = 0 for kq < lane
+                    x[i] = -s * xd[o + i];
                 }
-                for (; k < r; k += 2) s0 = fma(S[r * PLD + k], S[c * PLD + k], s0);
             }
-            double tot = s0 + s1;
-            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-            if (r > c && h == 0) S[c * PLD + r] = -tot / S[r * PLD + r];
-            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i > lane) S[(o + lane) * PLD + o + i] = x[i];
         }
     }
     __syncthreads();
+    inv_level<16, 2, 2>(S, T, tid);
+    inv_level<32, 2, 4>(S, T, tid);
+    inv_level<64, 4, 4>(S, T, tid);
     for (int e = tid; e < NB * NB; e += blockDim.x) {
         const int r = e >> 7, c = e & (NB - 1);
         linv[e] = (c < r) ? S[c * PLD + r] : (c == r ? xd[r] : 0.0);
     }
     // log det: fixed-order tree reduction (deterministic)
-    if (tid < NB) {
-        const double l = S[tid * PLD + tid];
-        red[tid] = (k0 + tid < Mtrue) ? log(l * l) : 0.0;     // inversion.py:108: log(diag(L)**2)
-    }
-    __syncthreads();
     for (int o = NB / 2; o > 0; o >>= 1) {
         if (tid < o) red[tid] += red[tid + o];
         __syncthreads();
@@ -145,7 +227,7 @@ static gemm::Task make_task(const double* A, long lda, const double* B, long ldb
 
 cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, cudaStream_t s) {
     static bool attr_set = false;
-    const int smem = NB * PLD * (int)sizeof(double);
+    const int smem = (NB * PLD + 64 * 64 + NB) * (int)sizeof(double);
     cudaError_t e;
     if (!attr_set) {
         e = cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
