@@ -325,6 +325,7 @@ struct gb_problem {
     uint8_t* b8 = nullptr;
     int* b_exp = nullptr;
     double* partial = nullptr;           // [Mp/128][ldp]
+    double* vscratch = nullptr;          // running sums of V when Mp > 16384 (several accumulator flushes)
     int var_slices = 0;
     size_t b8_bytes = 0;
     // fp64 matrix-free refinement scratch
@@ -359,7 +360,7 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
     void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
                     p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp,
                     p->Linv, p->tmpL, p->alpha, p->l8, p->l_exp, p->b8, p->b_exp, p->partial,
-                    p->rf_w, p->rf_z, p->rf_part, p->rf_t,
+                    p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch,
                     p->linv, p->scal, p->info, p->mu, p->var};
     for (void* q : ptrs)
         if (q) gb_dev_free(p->ctx, q);
@@ -696,7 +697,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     w.linv = p->linv; w.logdet = p->scal; w.info = p->info;
     GB_CUDA(ctx, chol_factor(p->Bm, Mp, (int)Mp, (int)M, w, s));
     GB_CUDA(ctx, cudaEventRecord(p->ev[6], s));
-    const bool int8_var = full && h->slices != 0 && Mp <= 16384;
+    const bool int8_var = full && h->slices != 0;
     if (!int8_var) {
         GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->ysol, 16, 1, p->ytmp, s));
         dot_self_kernel<<<1, 256, 0, s>>>(p->ysol, M, p->scal + 1);
@@ -725,6 +726,9 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
                 p->bytes += 2 * (size_t)Mp * Mp * 8 + (size_t)(Mp / 128) * ldp * 8;
             }
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->l8, (size_t)ozaki_rows_bytes(Mp, Mp, S)));
+            if (p->vscratch) { gb_dev_free(ctx, p->vscratch); p->vscratch = nullptr; }
+            if (ozaki_colsumsq_scratch_bytes((int)Mp, S, ctx->sm_count))
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->vscratch, (size_t)ozaki_colsumsq_scratch_bytes((int)Mp, S, ctx->sm_count)));
             p->bytes += (size_t)ozaki_rows_bytes(Mp, Mp, S);
             p->var_slices = S;
         }
@@ -759,7 +763,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         if (nref > 0) GB_CUDA(ctx, refine_dot(p->ydev, p->alpha, M, p->scal + 1, s));    // u.u = y^T (AkA)^-1 y with the refined alpha
         GB_CUDA(ctx, ozaki_slice_sens(p->Linv, Mp, Mp, Mp, S, p->l_exp, p->l8, Mp, s));
         GB_CUDA(ctx, ozaki_slice_cols_mean(p->Pt, Mp, ldp, ldp, S, p->b_exp, p->b8, p->alpha, nullptr, ncp, ncol, s));
-        GB_CUDA(ctx, ozaki_colsumsq_tri(p->l8, p->l_exp, p->b8, p->b_exp, (int)Mp, ldp, S, p->partial, ctx->sm_count, s));
+        GB_CUDA(ctx, ozaki_colsumsq_tri(p->l8, p->l_exp, p->b8, p->b_exp, (int)Mp, ldp, S, p->partial, p->vscratch, ctx->sm_count, s));
         GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
         GB_CUDA(ctx, ozaki_var_finalize(p->partial, (int)(Mp / 128), ldp, ncp, ncol, h->gp_amp, p->var, s));
         p->nlaunch += 10;

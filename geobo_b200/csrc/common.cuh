@@ -141,6 +141,7 @@ struct OzakiArgs {
     int Ns, ncol, c0;
 };
 int ozaki_tile_n(int slices);
+int ozaki_chunk();
 long ozaki_table_bytes(long ext, int slices);
 long ozaki_rows_bytes(long rows, long kp, int slices, int tr = 128);
 cudaError_t ozaki_slice_rows(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp, int tr,
@@ -153,8 +154,9 @@ cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStre
 long ozaki_cols_bytes(long cols, long kp, int slices);
 cudaError_t ozaki_slice_cols_mean(const double* X, long rows, long cols, long ld, int slices, int* exps, uint8_t* out,
                                   const double* alpha, double* mu, long ncp, long ncol, cudaStream_t s);
+long ozaki_colsumsq_scratch_bytes(int Mp, int slices, int sm_count);
 cudaError_t ozaki_colsumsq_tri(const uint8_t* a8, const int* a_exp, const uint8_t* b8, const int* b_exp, int Mp, long ncols,
-                               int slices, double* partial, int sm_count, cudaStream_t s);
+                               int slices, double* partial, double* scratch, int sm_count, cudaStream_t s);
 cudaError_t ozaki_gemm_store(const uint8_t* a8, const int* a_exp, int a_ksteps, int a_k0, const uint8_t* b8, const int* b_exp,
                              int b_ksteps, int b_k0, int ksteps, int M, int N, double* C, long ldc, int lower, int slices,
                              int sm_count, cudaStream_t s);

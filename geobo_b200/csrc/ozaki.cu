@@ -24,6 +24,8 @@
 //     lane picks its own unaligned 16-byte window with five shuffles + funnel shifts and stores it straight into
 //     the canonical layout (one conflict-free 16-byte st.shared per lane, digit and 16-column segment).
 // Stage hand-off is mbarrier based (full: producer warp + bulk-copy bytes -> MMA, empty: tcgen05.commit -> producer).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 #include "ozaki.cuh"
@@ -319,6 +321,22 @@ static cudaError_t launch_one(const Params& P, int sm_count, cudaStream_t s) {
 }  // namespace ozaki
 
 // ------------------------------------------------------------------------------------------------ host entry points
+// Accumulator flush interval in contraction indices: level S-1 sums S products of balanced digits (|d| <= 128), so
+// S * 2^14 * chunk < 2^31 holds for chunk = 16384 and S <= 7.  GEOBO_B200_CHUNK (multiple of 32, <= 16384) shortens it
+// so that tests can exercise the multi-flush code paths on small cubes.
+int ozaki_chunk() {
+    static int chunk = 0;
+    if (!chunk) {
+        chunk = 16384;
+        const char* e = getenv("GEOBO_B200_CHUNK");
+        if (e) {
+            const int v = atoi(e);
+            if (v >= 32 && v <= 16384 && v % 32 == 0) chunk = v;
+        }
+    }
+    return chunk;
+}
+
 int ozaki_tile_n(int slices) { return slices == 4 ? ozaki::Cfg<4>::NT : slices == 5 ? ozaki::Cfg<5>::NT : slices == 6 ? ozaki::Cfg<6>::NT : 0; }
 
 // bytes of the pre-tiled digit blocks of a rows x kp operand with `tr` rows per tile (128: M side, tile_n: N side)
@@ -361,7 +379,7 @@ cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStre
     P.t8 = a.t8; P.t_exp = a.t_exp; P.L = a.L; P.Pt = a.Pt;
     P.ext = a.ext; P.C0 = a.C0; P.kp = a.kp; P.ldp = a.ldp; P.ncp = a.ncp;
     P.Ns = a.Ns; P.ncol = a.ncol; P.c0 = a.c0;
-    P.chunk = 16384;       // int32 overflow bound: level S-1 sums S products of balanced digits, S * 2^14 * chunk < 2^31 for S <= 7
+    P.chunk = ozaki_chunk();
     P.n_stile = (a.Ns + 127) / 128;
     P.n_itile = 0;
     switch (slices) {

@@ -116,6 +116,7 @@ struct GemmParams {
     const int* b_exp;       // [N]
     double* C;              // EPI_STORE: [M][ldc]
     double* partial;        // EPI_SUMSQ: [n_mtile][ldc]
+    double* scratch;        // EPI_SUMSQ with more than one accumulator flush: [grid][128][NT] running fp64 sums of V
     long ldc;
     int M, N;               // valid rows / columns
     int a_ksteps, b_ksteps; // K steps per tile row of the stored operands
@@ -264,12 +265,23 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(const __grid_constan
                                 if (n0t + n0 + k < P.N) crow[k] = (k0 == 0) ? val[k] : crow[k] + val[k];
                         }
                     } else {
+                        const bool last = k0 + P.chunk_steps >= kend;
+                        if (kend > P.chunk_steps) {          // V accumulates over several flushes before it is squared
+                            double* sc = P.scratch + ((size_t)blockIdx.x * 128 + row) * NT + n0;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                if (k0 > 0) val[k] += sc[k];
+                                if (!last) sc[k] = val[k];
+                            }
+                        }
+                        if (last) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             double sq = val[k] * val[k];
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
                             if (lane == 0) part[warp][n0 + k] = sq;
+                        }
                         }
                     }
                 }
@@ -332,15 +344,20 @@ cudaError_t ozaki_slice_cols_mean(const double* X, long rows, long cols, long ld
 }
 
 // partial[mt][n] = sum over the 128 rows of tile mt of (Linv . Pt)[m, n]^2
+long ozaki_colsumsq_scratch_bytes(int Mp, int slices, int sm_count) {
+    return Mp > ozaki_chunk() ? (long)sm_count * 128 * ozaki_tile_n(slices) * 8 : 0;
+}
+
 cudaError_t ozaki_colsumsq_tri(const uint8_t* a8, const int* a_exp, const uint8_t* b8, const int* b_exp, int Mp, long ncols, int slices,
-                               double* partial, int sm_count, cudaStream_t s) {
+                               double* partial, double* scratch, int sm_count, cudaStream_t s) {
     ozaki::GemmParams P;
     memset(&P, 0, sizeof P);
     P.a8 = a8; P.a_exp = a_exp; P.b8 = b8; P.b_exp = b_exp; P.partial = partial; P.ldc = ncols;
     P.M = Mp; P.N = (int)ncols;
     P.a_ksteps = P.b_ksteps = P.ksteps = Mp / 32;
-    P.chunk_steps = 16384 / 32;
-    if (P.ksteps > P.chunk_steps) return cudaErrorInvalidValue;     // single accumulator flush only (M <= 16384)
+    P.chunk_steps = ozaki_chunk() / 32;
+    P.scratch = scratch;
+    if (P.ksteps > P.chunk_steps && !scratch) return cudaErrorInvalidValue;
     P.tri = 1;
     switch (slices) {
         case 4: return ozaki::launch_gemm<4, ozaki::EPI_SUMSQ>(P, sm_count, s);
@@ -357,7 +374,7 @@ cudaError_t ozaki_gemm_store(const uint8_t* a8, const int* a_exp, int a_ksteps, 
     memset(&P, 0, sizeof P);
     P.a8 = a8; P.a_exp = a_exp; P.b8 = b8; P.b_exp = b_exp; P.C = C; P.ldc = ldc;
     P.M = M; P.N = N; P.a_ksteps = a_ksteps; P.b_ksteps = b_ksteps; P.a_k0 = a_k0; P.b_k0 = b_k0; P.ksteps = ksteps;
-    P.chunk_steps = 16384 / 32;
+    P.chunk_steps = ozaki_chunk() / 32;
     P.lower = lower;
     switch (slices) {
         case 4: return ozaki::launch_gemm<4, ozaki::EPI_STORE>(P, sm_count, s);

@@ -82,3 +82,35 @@ def test_int8_full_size_32cube_vs_fp64_path(ctx):
     assert np.abs(mu3 - (2.0 * mu1 - 0.5 * mu2)).max() < 1e-8 * scale
     assert np.array_equal(var1, var2)
     prob.close()
+
+
+def test_int8_multi_flush_paths_match_single_flush(ctx):
+    """GEOBO_B200_CHUNK=256 forces several accumulator flushes per tile (projection read-modify-write, AkA store,
+    running sums of V before the squares) on a small cube; the result must equal the single-flush run up to fp64
+    summation order.  Runs in a subprocess because the interval is read once per process."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r'''
+import sys, json, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+from geobo_b200 import config_loader, inversion, synth
+cfg = synth.settings(12, 11, 32, kernelfunc="matern32", precision="int8x5")
+config_loader.load_settings(cfg, make_outpath=False)
+f = synth.make_inputs(nd=6, seed=2)
+inv = inversion.Inversion(); inv.create_cubegeometry()
+inv.gp_length = inv.gp_length * np.array([1.0, 1.01, 1.02])
+out = inv.cubing(f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"])
+np.save(sys.argv[1], np.stack(out))
+''' % (ROOT, ROOT)
+    import tempfile
+    res = []
+    for chunk in ("16384", "256"):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as tf:
+            env = dict(os.environ, GEOBO_B200_CHUNK=chunk)
+            r = subprocess.run([sys.executable, "-c", code, tf.name], env=env, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            res.append(np.load(tf.name))
+    for a, b in zip(res[0], res[1]):
+        assert np.abs(a - b).max() <= 1e-11 * np.abs(a).max()
