@@ -171,6 +171,9 @@ def run_ours(args):
     value = N * args.steps / dev_s
     stage_ms = {k: v / args.steps for k, v in stage_ms.items() if k != "launches"}
 
+    device_bytes = prob.device_bytes()
+    prob.close()      # its buffers go to the context's cache and are reused by the end-to-end problem below (one cube resident at a time)
+
     # ---------------- end to end through Inversion.cubing (host arrays in, six host cubes out) ----------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     dist.barrier()
@@ -243,8 +246,8 @@ def run_ours(args):
            "config": {"workload": wl["name"], "workload_id": args.workload, "voxels": N, "sensors_per_survey": Ns, "drill_rows": nd,
                       "data_rows_M": M, "kernel": wl["kernel"], "precision": args.precision + (" + %d refinement step(s)" % args.refine if slices else ""),
                       "parallelism": "voxel-column shards of Pt x%d" % world,
-                      "l2": "inputs larger than L2 (A and Pt are %.1f GB)" % (prob.device_bytes() / 1e9),
-                      "device_bytes": prob.device_bytes()},
+                      "l2": "inputs larger than L2 (A and Pt are %.1f GB)" % (device_bytes / 1e9),
+                      "device_bytes": device_bytes},
            "wall_ms_per_step": wall_s * 1e3 / args.steps, "stage_ms": stage_ms, "a_sens_ms": t_sens_ms,
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "roofline": roofline,
            "logl": logl, "info": info_pd, "finite": finite, "gpu": info["name"]}

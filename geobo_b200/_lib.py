@@ -49,6 +49,7 @@ _SIGNATURES = {
                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gb_comm_unique_id": (C.c_int, [_P, _P]),
     "gb_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "gb_comm_allgather": (C.c_int, [_P, _P, C.c_int64, _P]),
     "gb_grid_points": (C.c_int, [_P, _P, _P, _P]),
     "gb_sqdist": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
     "gb_create_cov": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int, _P]),
@@ -142,6 +143,13 @@ class Context:
         buf = C.create_string_buffer(bytes(uid), 128)
         self.check(self.lib.gb_comm_init(self.h, buf, int(rank), int(nranks)))
         self.rank, self.nranks = int(rank), int(nranks)
+
+    def allgather(self, local):
+        """NCCL all-gather of equally sized float64 host arrays: returns (nranks, local.size)."""
+        loc = _f64(local).ravel()
+        out = np.empty((max(1, getattr(self, "nranks", 1)), loc.size))
+        self.check(self.lib.gb_comm_allgather(self.h, _ptr(loc), int(loc.size), _ptr(out)))
+        return out
 
     # ---- geobo/kernels.py
     def grid_points(self, lpix, pixscale):

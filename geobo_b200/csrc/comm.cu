@@ -11,6 +11,7 @@ typedef struct { char internal[128]; } ncclUniqueId_;
 typedef int (*fn_getuid)(ncclUniqueId_*);
 typedef int (*fn_initrank)(void**, int, ncclUniqueId_, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_destroy)(void*);
 typedef const char* (*fn_errstr)(int);
 
@@ -19,6 +20,7 @@ struct NcclApi {
     fn_getuid get_uid = nullptr;
     fn_initrank init_rank = nullptr;
     fn_allreduce all_reduce = nullptr;
+    fn_allgather all_gather = nullptr;
     fn_destroy destroy = nullptr;
     fn_errstr errstr = nullptr;
 } g_nccl;
@@ -34,6 +36,7 @@ int load_nccl(gb_ctx* ctx) {
     g_nccl.get_uid = (fn_getuid)dlsym(g_nccl.handle, "ncclGetUniqueId");
     g_nccl.init_rank = (fn_initrank)dlsym(g_nccl.handle, "ncclCommInitRank");
     g_nccl.all_reduce = (fn_allreduce)dlsym(g_nccl.handle, "ncclAllReduce");
+    g_nccl.all_gather = (fn_allgather)dlsym(g_nccl.handle, "ncclAllGather");
     g_nccl.destroy = (fn_destroy)dlsym(g_nccl.handle, "ncclCommDestroy");
     g_nccl.errstr = (fn_errstr)dlsym(g_nccl.handle, "ncclGetErrorString");
     if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.all_reduce || !g_nccl.destroy)
@@ -73,6 +76,30 @@ int comm_allreduce_sum_f64(gb_ctx* ctx, double* buf, size_t count) {
     const int ncclFloat64 = 8, ncclSum = 0;
     int rc = g_nccl.all_reduce(buf, buf, count, ncclFloat64, ncclSum, ctx->nccl_comm, ctx->stream);
     if (rc != 0) return gb_fail(ctx, GB_ERR_NCCL, "ncclAllReduce: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    return GB_OK;
+}
+
+// Gathers `count` doubles per rank (host buffers; staged through device memory, NCCL over NVLink): out[r * count ...] = rank r's data.
+// Used for the 6 N result values (mean / variance shards) so that every rank returns whole cubes from Inversion.cubing.
+extern "C" int gb_comm_allgather(gb_ctx* ctx, const double* local, int64_t count, double* out) {
+    if (!ctx || !local || !out || count < 1) return gb_fail(ctx, GB_ERR_ARG, "gb_comm_allgather: bad argument");
+    if (ctx->nranks <= 1) {
+        memcpy(out, local, (size_t)count * sizeof(double));
+        return GB_OK;
+    }
+    if (!ctx->nccl_comm || !g_nccl.all_gather) return gb_fail(ctx, GB_ERR_NCCL, "gb_comm_allgather without gb_comm_init");
+    GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *send = nullptr, *recv = nullptr;
+    GB_CUDA(ctx, gb_dev_malloc(ctx, &send, (size_t)count * sizeof(double)));
+    GB_CUDA(ctx, gb_dev_malloc(ctx, &recv, (size_t)count * ctx->nranks * sizeof(double)));
+    GB_CUDA(ctx, cudaMemcpyAsync(send, local, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int ncclFloat64 = 8;
+    int rc = g_nccl.all_gather(send, recv, (size_t)count, ncclFloat64, ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return gb_fail(ctx, GB_ERR_NCCL, "ncclAllGather: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    GB_CUDA(ctx, cudaMemcpyAsync(out, recv, (size_t)count * ctx->nranks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    gb_dev_free(ctx, send);
+    gb_dev_free(ctx, recv);
     return GB_OK;
 }
 

@@ -71,12 +71,25 @@ def max_over_ranks(value):
     return float(t[0])
 
 
-def allgather_columns(local, n_vox, align=128):
-    """``local``: (k, ncol_local) array of this rank's voxel columns -> (k, n_vox) on every rank."""
+def allgather_columns(local, n_vox, align=128, ctx=None):
+    """``local``: (k, ncol_local) array of this rank's voxel columns -> (k, n_vox) on every rank.
+    With a ``_lib.Context`` that has an NCCL communicator the gather runs over NCCL/NVLink inside the library
+    (``gb_comm_allgather``); otherwise over the host control plane (gloo)."""
     world, rk = _state["world"], _state["rank"]
     local = np.ascontiguousarray(local, dtype=np.float64)
     if world <= 1:
         return local
+    if ctx is not None and getattr(ctx, "nranks", 1) == world:
+        k = local.shape[0]
+        per = shard_columns(n_vox, world, 0, align)[1]
+        buf = np.zeros((k, per))
+        buf[:, :local.shape[1]] = local
+        outs = ctx.allgather(buf).reshape(world, k, per)
+        full = np.empty((k, n_vox))
+        for r in range(world):
+            c0, c1 = shard_columns(n_vox, world, r, align)
+            full[:, c0:c1] = outs[r][:, :c1 - c0]
+        return full
     import torch
     import torch.distributed as td
     k = local.shape[0]

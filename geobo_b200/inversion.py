@@ -131,7 +131,7 @@ class Inversion:
             sys.exit(1)
         N = self._problem.N
         if _dist.world_size() > 1:
-            both = _dist.allgather_columns(np.vstack([mu, var]), N)
+            both = _dist.allgather_columns(np.vstack([mu, var]), N, ctx=self._problem.ctx)
             mu, var = both[:3], both[3:]
         self._lazy = {}
         mu = np.ascontiguousarray(mu).reshape(3 * N)

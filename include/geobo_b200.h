@@ -85,6 +85,9 @@ int gb_device_info(gb_ctx* ctx, char* name, int name_len, int* sm_count, int* cc
  * the host distributes it (e.g. torch.distributed / a file) and every rank calls gb_comm_init. */
 int gb_comm_unique_id(gb_ctx* ctx, void* id128);
 int gb_comm_init(gb_ctx* ctx, const void* id128, int rank, int nranks);
+/* out[r * count + i] = rank r's local[i] (host buffers, NCCL all-gather over NVLink): gathers the mean / variance shards so
+ * that Inversion.cubing returns whole cubes on every rank.  Single rank: a copy. */
+int gb_comm_allgather(gb_ctx* ctx, const double* local, int64_t count, double* out);
 
 /* ------------------------------------------------------------------ geobo/kernels.py */
 /* kernels.calcGridPoints3D(Lpix, pixscale)  (kernels.py:27-42): out[(iy*xN+ix)*zN+iz][0..2] */
