@@ -59,17 +59,54 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons / power sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is
+    polled in-process every 10 ms (no process spawn inside or next to the timed region: starting `nvidia-smi` takes
+    NVML/driver locks for hundreds of ms on a multi-GPU box and stalls the CUDA calls of every rank); `nvidia-smi
+    -lms` is the fallback when the NVML bindings are missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    _nvml = None
+
+    @classmethod
+    def init(cls):
+        """Call once before any timed region."""
+        if cls._nvml is None:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                cls._nvml = pynvml
+            except Exception:
+                cls._nvml = False
+        return cls._nvml
 
     def __init__(self, device):
         self.device = device
         self.rows = []
         self.proc = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.device])
+            except Exception:
+                pass
+        return self.device
 
     def start(self):
+        nv = self.init()
+        if nv:
+            try:
+                self.handle = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+                self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
@@ -79,18 +116,36 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        nv = self._nvml
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.rows.append([str(self.device), sm, self.max_sm, pw, ""] + ["Active" if mask & bit else "Not Active" for _, bit in names])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([t.strip() for t in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        elif self.thread:
+            self.thread.join(timeout=1)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         sm, mx, reasons, power = [], [], set(), []
         for r in self.rows:
             try:
@@ -98,7 +153,7 @@ class ClockSampler:
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
+                if str(v).lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
@@ -147,6 +202,7 @@ def run_ours(args):
     prob.set_data(y)
     h = prob.hyper(gl_eff, config_loader.gp_err, config_loader.gp_coeff, 1.0, wl["kernel"], slices=slices, refine=args.refine)
     t_sens_ms = prob.timings()["a_sens"]
+    ClockSampler.init()
     for _ in range(args.warmup):
         prob.predict(h, want_host=False)
     sampler = ClockSampler(ctx_device())

@@ -4,13 +4,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import bench
-from geobo_b200 import _lib, config_loader, inversion, synth
+from geobo_b200 import _lib, config_loader, dist, inversion, synth
 
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
 xN, yN, zN = wl["shape"]
 cfg = synth.settings(xN, yN, zN, kernelfunc=wl["kernel"], precision="int8x5")
 config_loader.load_settings(cfg, make_outpath=False)
 ctx = _lib.default_context()
+rank, world = dist.init_from_env(ctx)
 f = synth.make_inputs(nd=wl["nd"], seed=0, ctx=ctx)
 inv = inversion.Inversion()
 inv.create_cubegeometry()
@@ -23,6 +24,8 @@ def timed(name, fn):
     return w
 inv._build_problem = timed("build_problem", orig_build)
 inv.predict3 = timed("predict3", orig_predict)
+dist.allgather_columns = timed("allgather", dist.allgather_columns)
+_lib.Problem.predict = timed("problem.predict", _lib.Problem.predict)
 for it in range(4):
     acc.clear()
     inv.gp_length = gl0.copy()
@@ -30,5 +33,6 @@ for it in range(4):
     inv.cubing(f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"])
     tot = time.perf_counter() - t
     tm = inv.timings
-    print("iter %d: cubing %.1f ms | build_problem %.1f  predict3 %.1f | device total %.1f (project %.1f)"
-          % (it, tot * 1e3, acc["build_problem"] * 1e3, acc["predict3"] * 1e3, tm["total"], tm["project"]), flush=True)
+    print("rank %d iter %d: cubing %.1f ms | build_problem %.1f  predict3 %.1f (problem.predict %.1f, allgather %.1f) | device total %.1f (project %.1f)"
+          % (rank, it, tot * 1e3, acc["build_problem"] * 1e3, acc["predict3"] * 1e3, acc.get("problem.predict", 0) * 1e3, acc.get("allgather", 0) * 1e3,
+             tm["total"], tm["project"]), flush=True)
