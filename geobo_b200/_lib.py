@@ -65,6 +65,8 @@ _SIGNATURES = {
     "gb_neg_logl": (C.c_int, [_P, C.POINTER(Hyper), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "gb_problem_get_sens": (C.c_int, [_P, C.c_int, _P]),
     "gb_forward": (C.c_int, [_P, C.c_int, _P, _P]),
+    "gb_acquisition_vertical": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, C.c_double, _P]),
+    "gb_acquisition_drill": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _P, C.c_int64, C.c_double, C.c_double, _P]),
     "gb_posterior_cov": (C.c_int, [_P, C.POINTER(Hyper), _P]),
     "gb_get_timings": (C.c_int, [_P, _P, C.c_int]),
     "gb_problem_device_bytes": (C.c_uint64, [_P]),
@@ -143,6 +145,27 @@ class Context:
         buf = C.create_string_buffer(bytes(uid), 128)
         self.check(self.lib.gb_comm_init(self.h, buf, int(rank), int(nranks)))
         self.rank, self.nranks = int(rank), int(nranks)
+
+    # ---- geobo/run_geobo.py acquisition functions
+    def acquisition_vertical(self, rec, var, kappa, beta, costs=None):
+        rec, var = _f64(rec), _f64(var)
+        shp = np.ascontiguousarray(rec.shape, dtype=np.int64)
+        cst = _f64(costs) if costs is not None else None
+        out = np.empty(rec.shape[:2])
+        self.check(self.lib.gb_acquisition_vertical(self.h, _ptr(rec), _ptr(var), _ptr(cst) if cst is not None else None, _ptr(shp),
+                                                    float(kappa), float(beta), _ptr(out)))
+        return out
+
+    def acquisition_drill(self, rec, var, voxsize, zmax, length, params, kappa, beta, costs=None):
+        rec, var = _f64(rec), _f64(var)
+        shp = np.ascontiguousarray(rec.shape, dtype=np.int64)
+        cst = _f64(costs) if costs is not None else None
+        prm = _f64(params).reshape(-1, 4)
+        vs = _f64(voxsize)
+        out = np.empty(prm.shape[0])
+        self.check(self.lib.gb_acquisition_drill(self.h, _ptr(rec), _ptr(var), _ptr(cst) if cst is not None else None, _ptr(shp), _ptr(vs),
+                                                 float(zmax), float(length), _ptr(prm), int(prm.shape[0]), float(kappa), float(beta), _ptr(out)))
+        return out
 
     def allgather(self, local):
         """NCCL all-gather of equally sized float64 host arrays: returns (nranks, local.size)."""

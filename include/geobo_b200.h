@@ -168,6 +168,20 @@ int gb_neg_logl(gb_problem* p, const gb_hyper* h, double* neg_logl, int* info);
 int gb_problem_get_sens(gb_problem* p, int kind, double* out);
 /* simcube.create_synsurvey (simcube.py:147-150): out[nsens] = A_kind . x[N] */
 int gb_forward(gb_problem* p, int kind, const double* x, double* out);
+
+/* ------------------------------------------------------------------ geobo/run_geobo.py (acquisition)
+ * Exhaustive evaluation of the Bayesian-optimisation utility the reference feeds to scipy.optimize.shgo.
+ * gb_acquisition_vertical: futility_vertical (run_geobo.py:175-200) for every column (a, b) of the (n0, n1, n2) cubes:
+ *   out[a*n1 + b] = sum_z rec + kappa * sqrt(sum_z var) - beta * sum_z costs  for 0 < a < n0-1, 0 < b < n1-1, -inf elsewhere
+ *   (the positive utility; the reference returns its negative).  costs may be NULL (zeros).
+ * gb_acquisition_drill: futility_drill (run_geobo.py:203-235) for n candidates params[i] = (x0, y0, azimuth, dip):
+ *   ray of `length` from (x0, y0, zmax), int(2*length/min(voxsize)) samples, voxel index (int(x/vx), int(y/vy), int(-z/vz))
+ *   on axes (0, 1, 2), negative indices wrap as in NumPy, out[i] = 0 when the ray leaves the cube (the reference's except). */
+int gb_acquisition_vertical(gb_ctx* ctx, const double* rec, const double* var, const double* costs, const int64_t shape[3],
+                            double kappa, double beta, double* out);
+int gb_acquisition_drill(gb_ctx* ctx, const double* rec, const double* var, const double* costs, const int64_t shape[3],
+                         const double voxsize[3], double zmax, double length, const double* params, int64_t n, double kappa,
+                         double beta, double* out);
 /* Dense posterior covariance block (small cubes only; inversion.py:117): out (3N x 3N). */
 int gb_posterior_cov(gb_problem* p, const gb_hyper* h, double* out);
 int gb_get_timings(gb_problem* p, double* ms, int n);

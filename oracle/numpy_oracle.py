@@ -514,3 +514,52 @@ def cylinders_truth(c, voxelpos):
     density[rc1 <= rad ** 2] = 1.0
     density[(x3 < c.xLcube / 5.0) | (x3 > c.xLcube * 4.0 / 5.0)] = 0.1
     return density, c.gp_coeff[1] * density
+
+
+# ------------------------------------------------------------------------------------------------ acquisition
+def spherical2cartes(x0, y0, z0, phi, theta, r):
+    """geobo/utils.py:21-37"""
+    return x0 + r * np.sin(theta) * np.cos(phi), y0 + r * np.sin(theta) * np.sin(phi), z0 + r * np.cos(theta)
+
+
+def futility_vertical(params, drill_rec, drill_var, kappa, beta, costs=None):
+    """geobo/run_geobo.py:175-200 (module globals made explicit)."""
+    if costs is None:
+        costs = drill_rec * 0.
+    params = np.asarray(params)
+    xmaxvox = drill_rec.shape[0] - 1
+    ymaxvox = drill_rec.shape[1] - 1
+    if np.isfinite(params).all():
+        xd = int(np.round(params[0]))
+        yd = int(np.round(params[1]))
+        if (xd > 0) & (xd < xmaxvox) & (yd > 0) & (yd < ymaxvox):
+            func = np.sum(drill_rec[xd, yd, :]) + kappa * np.sqrt(np.sum(drill_var[xd, yd, :])) - beta * np.sum(costs[xd, yd, :])
+        else:
+            func = -np.inf
+    else:
+        func = -np.inf
+    return -func
+
+
+def futility_drill(params, drill_rec, drill_var, kappa, beta, c, costs=None):
+    """geobo/run_geobo.py:203-235 (``c``: config with voxel sizes, zLcube, zmax)."""
+    if costs is None:
+        costs = drill_rec * 0.
+    length_newdrill = c.zLcube
+    x0, y0, azimuth, dip = params
+    nstep = int(2 * length_newdrill / np.min([c.xvoxsize, c.yvoxsize, c.zvoxsize]))
+    rladder = np.linspace(0, length_newdrill, nstep)
+    x0 = rladder * 0 + x0
+    y0 = rladder * 0 + y0
+    z0 = rladder * 0 + c.zmax
+    azimuth = rladder * 0 + azimuth
+    dip = rladder * 0 + dip
+    try:
+        xd, yd, zd = spherical2cartes(x0, y0, z0, azimuth * np.pi / 180., (180 - dip) * np.pi / 180., rladder)
+        xnew = (xd / c.xvoxsize).astype(int)
+        ynew = (yd / c.yvoxsize).astype(int)
+        znew = (-zd / c.zvoxsize).astype(int)
+        funct = np.sum(drill_rec[xnew, ynew, znew]) + kappa * np.sqrt(np.sum(drill_var[xnew, ynew, znew])) - beta * np.sum(costs[xnew, ynew, znew])
+    except Exception:
+        funct = 0.
+    return -funct

@@ -13,6 +13,7 @@ Outputs (``tests/golden/*.npz``):
   kernels_small.npz   create_cov / calcGridPoints3D / calcDistanceMatrix on a 4x3x2 grid
   sens_8x6x5.npz      A_sens('grav'|'magn') + A_drill on an 8x6x5 cube
   cubing_<k>_<tag>.npz  full Inversion.cubing on 8x6x5 (k in exp, sparse, matern32; nd>0 and nd=0)
+  acquisition.npz     futility_vertical / futility_drill (run_geobo.py:175-235) on random 10x12x8 cubes
   example1.npz / example2.npz
                       the five ``cubing`` inputs the reference's own driver
                       (``geobo/run_geobo.py:396-415``) produced from the committed
@@ -147,6 +148,43 @@ def job_cubing_small(kernelfunc, nd, gl_mult=None, tag=None):
     print("cubing", kernelfunc, tag, "logl", inv.logl, "gl_after", inv.gp_length)
 
 
+def job_acquisition():
+    """futility_vertical / futility_drill of the UNMODIFIED reference (geobo/run_geobo.py:175-235): the two function
+    definitions are extracted from the reference source with ``ast`` (the module itself is a script that runs the
+    whole pipeline at import) and executed with the module globals they read set explicitly."""
+    import ast
+    import numpy as np
+    from oracle import ref_loader
+    mods = ref_loader.load(ref_loader.write_yaml(dict(xNcube=12, yNcube=10, zNcube=8)))
+    cl = mods["config_loader"]
+    src = open("/root/reference/geobo/run_geobo.py").read()
+    tree = ast.parse(src)
+    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("futility_vertical", "futility_drill")]
+    usrc = open("/root/reference/geobo/utils.py").read()
+    utree = ast.parse(usrc)
+    wanted = [n for n in utree.body if isinstance(n, ast.FunctionDef) and n.name == "spherical2cartes"] + wanted
+    rng = np.random.default_rng(7)
+    shape = (cl.yNcube, cl.xNcube, cl.zNcube)
+    rec = rng.standard_normal(shape)
+    var = rng.uniform(0.05, 1.0, shape)
+    costs = rng.uniform(0.0, 2.0, shape)
+    g = dict(np=np, drill_rec=rec, drill_var=var, kappa=1.5, beta=0.3, zLcube=cl.zLcube, zmax=cl.zmax,
+             xvoxsize=cl.xvoxsize, yvoxsize=cl.yvoxsize, zvoxsize=cl.zvoxsize)
+    exec(compile(ast.Module(body=wanted, type_ignores=[]), "reference_acquisition", "exec"), g)
+    pv = np.array([[a, b] for a in range(-1, shape[0] + 1) for b in range(-1, shape[1] + 1)], dtype=float)
+    pv = np.vstack([pv, [[2.4, 3.6], [np.nan, 1.0], [4.5, 5.5]]])
+    fv = np.array([g["futility_vertical"](p) for p in pv])
+    fvc = np.array([g["futility_vertical"](p, costs) for p in pv])
+    pd_ = np.column_stack([rng.uniform(0.0, shape[0] * cl.xvoxsize, 400), rng.uniform(0.0, shape[1] * cl.yvoxsize, 400),
+                           rng.uniform(0, 360, 400), rng.uniform(30, 90, 400)])
+    with np.errstate(all="ignore"):
+        fd = np.array([g["futility_drill"](p) for p in pd_])
+        fdc = np.array([g["futility_drill"](p, costs) for p in pd_])
+    np.savez_compressed(os.path.join(HERE, "acquisition.npz"), cfg=json.dumps(_cfg_dict(cl)), rec=rec, var=var, costs=costs,
+                        kappa=1.5, beta=0.3, pv=pv, fv=fv, fvc=fvc, pd=pd_, fd=fd, fdc=fdc)
+    print("acquisition.npz: %d vertical, %d drill candidates (%d inside the cube)" % (len(pv), len(pd_), int((fd != 0).sum())))
+
+
 def _install_driver_stubs():
     """Stub the plotting / raster / VTK dependencies of geobo/run_geobo.py (absent here)."""
     import types
@@ -260,6 +298,7 @@ JOBS = [
     ["cubing_small", "exp", "7"], ["cubing_small", "sparse", "7"], ["cubing_small", "matern32", "7"],
     ["cubing_small", "exp", "0"],
     ["example", "1"], ["example", "2"],
+    ["acquisition"],
 ]
 
 
@@ -283,6 +322,8 @@ def main(argv):
         job_cubing_small(kf, nd, gl_mult=[1.0, 1.01, 1.02] if kf == "matern32" else None)
     elif cmd == "example":
         job_example(argv[1])
+    elif cmd == "acquisition":
+        job_acquisition()
     else:
         raise SystemExit("unknown job %r" % (argv,))
 
