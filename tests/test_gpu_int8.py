@@ -114,3 +114,19 @@ np.save(sys.argv[1], np.stack(out))
             res.append(np.load(tf.name))
     for a, b in zip(res[0], res[1]):
         assert np.abs(a - b).max() <= 1e-11 * np.abs(a).max()
+
+
+def test_int8_calc_logl_vs_oracle(ctx):
+    """Inversion.calc_logl (inversion.py:125-152) through the slice path: the marginal likelihood only needs the
+    projection, AkA and the Cholesky (no refinement applies to log det), so the stated tolerance is the slice error."""
+    c = configure(base_cfg(), xNcube=6, yNcube=5, zNcube=16, kernelfunc="exp", precision="int8x6")
+    f = synthetic_inputs(c, 4)
+    inv, _ = run_cubing(f)
+    E, vp = o.cube_geometry(c)
+    A = [o.a_sens(c, c.magneticField * 0, f["sensor_locations"], E, "grav"), o.a_sens(c, c.magneticField, f["sensor_locations"], E, "magn")]
+    didx = o.drill_indices(f["drilldata0"])
+    for params in ([1.0, 2.0, 1.0, 0.2, 0.2], [1.7, 3.1, 0.6, 0.5, 0.9]):
+        ref = o.calc_logl(c, A, didx, inv.Fs3, params)
+        got = inv.calc_logl(params)
+        assert abs(got - ref) < 1e-6 * abs(ref)
+    assert inv.calc_logl([-1.0, 2.0, 1.0, 0.2, 0.2]) == np.inf
