@@ -3,6 +3,8 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "comm.h"
 
@@ -195,13 +197,21 @@ extern "C" int gb_create_cov_grid(gb_ctx* ctx, const int64_t ncube[3], const dou
     CovParams cp;
     GB_TRY(fill_cov_params(ctx, cp, kernel_id, gpl, w, amp));
     GB_CUDA(ctx, cudaSetDevice(ctx->device));
-    DevBuf<double> o;
+    DevBuf<double> o, tab;
+    DevBuf<int> lat;
     GB_CUDA(ctx, o.alloc(9 * N * N));
+    const int64_t ext = (2 * ncube[0] - 1) * (2 * ncube[1] - 1) * (2 * ncube[2] - 1);
+    const bool direct = getenv("GEOBO_B200_ASSEMBLY_DIRECT") != nullptr;     // per-element evaluation (kept for comparison)
+    if (!direct) {
+        if (ext >= (1LL << 31)) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "cube too large for 32-bit lattice ids");
+        GB_CUDA(ctx, tab.alloc(9 * ext));
+        GB_CUDA(ctx, lat.alloc(N));
+    }
     cudaEvent_t e0, e1;
     GB_CUDA(ctx, cudaEventCreate(&e0));
     GB_CUDA(ctx, cudaEventCreate(&e1));
     GB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-    GB_CUDA(ctx, launch_create_cov_grid(cp, ncube, vox, o.p, ctx->stream));
+    GB_CUDA(ctx, launch_create_cov_grid(cp, ncube, vox, o.p, ctx->stream, direct ? nullptr : tab.p, direct ? nullptr : lat.p));
     GB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     if (out) GB_CUDA(ctx, cudaMemcpyAsync(out, o.p, 9 * N * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -114,8 +114,9 @@ cudaError_t launch_cov_tables(const CovParams& cp, const int64_t ncube[3], const
                               cudaStream_t s);
 cudaError_t launch_lattice_ids(const int64_t ncube[3], int* L, int64_t n_padded, cudaStream_t s);
 cudaError_t launch_create_cov_dense(const CovParams& cp, const double* D2, int64_t n, double* out, cudaStream_t s);
+// tables ([9][ext]) and L ([N]) given: stationary tables + gather (HBM-write bound); null: per-element evaluation
 cudaError_t launch_create_cov_grid(const CovParams& cp, const int64_t ncube[3], const double vox[3], double* out,
-                                   cudaStream_t s);
+                                   cudaStream_t s, double* tables = nullptr, int* L = nullptr);
 cudaError_t launch_grid_points(const int64_t lpix[3], const double sc[3], double* out, cudaStream_t s);
 cudaError_t launch_sqdist(const double* pts, int64_t n, int dim, double* out, cudaStream_t s);
 cudaError_t launch_a_sens(int kind, const double B[3], const double* loc, int64_t nsens, const double* edges,

@@ -206,9 +206,86 @@ __global__ void __launch_bounds__(256) create_cov_grid_kernel(CovParams P, int x
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-cudaError_t launch_create_cov_grid(const CovParams& cp, const int64_t n[3], const double vox[3], double* out, cudaStream_t s) {
+// Same matrix assembled from the stationary-covariance tables: on the regular grid every block of create_cov depends only
+// on the lattice offset, so the 9 block functions are evaluated once per offset (cov_tables_kernel, 9 x 8N values instead
+// of 9 N^2 transcendental evaluations -- bit-identical, the same cov_value / lattice_d2 are used) and the dense 3N x 3N
+// matrix is a gather  out[(r,i),(c,j)] = tab[r*3+c][C0 + L(j) - L(i)].  One CTA owns the zN rows of one z-column ci of
+// one row block r: for a z-column cj of the contraction side the zN x zN output block is Toeplitz in ONE contiguous
+// table stretch of 2 zN - 1 values, so a chunk of CW columns needs CW (2 zN - 1) table loads for CW zN^2 outputs.  The
+// zN row segments of the chunk are built in shared memory and written with one bulk async store each (UBLKCP), double
+// buffered.  This turns the assembly from fp64-transcendental bound (0.17 of the HBM roofline) into HBM-write bound.
+__global__ void __launch_bounds__(256) create_cov_grid_gather_kernel(const double* __restrict__ tables, long ext, long C0, int xN,
+                                                                     int yN, int zN, int CW, double* __restrict__ out) {
+    extern __shared__ __align__(128) double sm[];
+    const int zs = 2 * zN - 1, ncolumns = xN * yN, seg = CW * zN;      // seg: doubles per row segment of one chunk
+    double* T = sm;                              // [CW][zs]
+    double* stage = sm + ((CW * zs + 15) & ~15); // [2][zN][seg]
+    const long N = (long)ncolumns * zN;
+    const int r = blockIdx.y, ci = blockIdx.x;
+    const int lci = (ci / xN) * (2 * xN - 1) + ci % xN;
+    const int nchunk = (ncolumns + CW - 1) / CW;
+    int buf = 0;
+    for (int c = 0; c < 3; ++c) {
+        const double* tab = tables + (long)(r * 3 + c) * ext + C0 - (zN - 1);
+        for (int ch = 0; ch < nchunk; ++ch, buf ^= 1) {
+            const int cj0 = ch * CW, ncj = min(CW, ncolumns - cj0);
+            // the bulk stores that last read this stage buffer (two chunks ago) must have finished reading shared memory
+            // (bulk groups are tracked per issuing thread: every one of the zN issuers waits for its own)
+            if (threadIdx.x < zN) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+            for (int e = threadIdx.x; e < ncj * zs; e += blockDim.x) {
+                const int cl = e / zs, k = e - cl * zs, cj = cj0 + cl;
+                const int lcj = (cj / xN) * (2 * xN - 1) + cj % xN;
+                T[cl * zs + k] = __ldg(tab + (long)(lcj - lci) * zs + k);      // table offsets jz - iz = k - (zN - 1)
+            }
+            __syncthreads();
+            double* st = stage + (long)buf * zN * seg;
+            for (int e = threadIdx.x; e < ncj * zN; e += blockDim.x) {
+                const int cl = e / zN, jz = e - cl * zN;
+                const double* t = T + cl * zs + jz + (zN - 1);
+                for (int iz = 0; iz < zN; ++iz) st[iz * seg + e] = t[-iz];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x < zN) {
+                const int iz = threadIdx.x;
+                double* dst = out + ((long)r * N + (long)ci * zN + iz) * 3 * N + (long)c * N + (long)cj0 * zN;
+                const unsigned bytes = (unsigned)(ncj * zN) * 8u;
+                if ((bytes & 15u) == 0 && (((uintptr_t)dst) & 15) == 0) {
+                    bulk_store(dst, st + iz * seg, bytes);
+                } else {
+                    for (int q = 0; q < ncj * zN; ++q) dst[q] = st[iz * seg + q];
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (threadIdx.x < zN) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// direct = true: evaluate the covariance function per element (reference order of work); false: tables + gather
+cudaError_t launch_create_cov_grid(const CovParams& cp, const int64_t n[3], const double vox[3], double* out, cudaStream_t s,
+                                   double* tables, int* L) {
     const long N = n[0] * n[1] * n[2];
-    create_cov_grid_kernel<<<(unsigned)(3 * N), 256, 0, s>>>(cp, (int)n[0], (int)n[1], (int)n[2], vox[0], vox[1], vox[2], out);
+    if (!tables || !L) {
+        create_cov_grid_kernel<<<(unsigned)(3 * N), 256, 0, s>>>(cp, (int)n[0], (int)n[1], (int)n[2], vox[0], vox[1], vox[2], out);
+        return cudaGetLastError();
+    }
+    const long ext = (2 * n[0] - 1) * (2 * n[1] - 1) * (2 * n[2] - 1);
+    const long C0 = ((n[1] - 1) * (2 * n[0] - 1) + (n[0] - 1)) * (2 * n[2] - 1) + (n[2] - 1);
+    cudaError_t e = launch_cov_tables(cp, n, vox, tables, s);
+    if (e != cudaSuccess) return e;
+    const int zN = (int)n[2], ncolumns = (int)(n[0] * n[1]);
+    if (zN > 256) return cudaErrorInvalidValue;
+    int CW = 4096 / (zN * zN);
+    if (CW < 1) CW = 1;
+    if (CW > ncolumns) CW = ncolumns;
+    const int smem = (((CW * (2 * zN - 1) + 15) & ~15) + 2 * zN * CW * zN) * (int)sizeof(double);
+    e = cudaFuncSetAttribute(create_cov_grid_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)ncolumns, 3);
+    create_cov_grid_gather_kernel<<<grid, 256, smem, s>>>(tables, ext, C0, (int)n[0], (int)n[1], zN, CW, out);
+    (void)L;
     return cudaGetLastError();
 }
 
