@@ -729,7 +729,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->l_exp, (size_t)Mp * sizeof(int)));
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->partial, (size_t)(Mp / 128) * ldp * sizeof(double)));
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_w, (size_t)3 * p->Kp * sizeof(double)));
-                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_z, (size_t)3 * ncp * sizeof(double)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_z, (size_t)8 * 3 * ncp * sizeof(double)));
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_part, (size_t)16 * p->Kp * sizeof(double)));
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_t, (size_t)3 * Mp * sizeof(double)));
                 GB_CUDA(ctx, cudaMemsetAsync(p->rf_t, 0, (size_t)3 * Mp * sizeof(double), s));

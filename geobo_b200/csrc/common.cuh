@@ -175,7 +175,8 @@ struct RefineArgs {
     int nsplit;
 };
 cudaError_t refine_at_alpha(const RefineArgs& a, const double* alpha, double* w /*[3][Kp]*/, cudaStream_t s);
-cudaError_t refine_kw(const RefineArgs& a, const double* w, double* z /*[3][ncp]*/, cudaStream_t s);
+int refine_kw_slices(long ncol);
+cudaError_t refine_kw(const RefineArgs& a, const double* w, double* z /*[refine_kw_slices][3][ncp]*/, cudaStream_t s);
 cudaError_t refine_a_z(const RefineArgs& a, const double* z, double* t /*[Mp]*/, cudaStream_t s);
 cudaError_t refine_residual(const double* y, const double* t, const double* alpha, long Ns, long M, long Mp, const double sigma[3],
                             double* r, cudaStream_t s);

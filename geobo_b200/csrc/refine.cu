@@ -48,24 +48,36 @@ __global__ void w_drill_kernel(const double* __restrict__ alpha_drill, const int
     if (d < nd) w2[drill[d]] = alpha_drill[d];
 }
 
-// z[r][i] = sum_c sum_j K[(r,i),(c,j)] w[c][j]  for the 16 consecutive voxels i = c0 + 16 seg .. (one z-column segment;
-// needs zN % 16 == 0 and c0 % 16 == 0).  K comes from the stationary tables: K[(r,i),(c,j)] = tab[c*3+r][C0 + L(j) - L(i)].
-// Block = 4 z-quads x 64 contraction-column groups; a thread owns 4 consecutive outputs and slides a 4-entry window of
-// the table along the contraction column (1 table load + 1/3 w load per 4 FMAs).
+// z[r][i] = sum_c sum_j K[(r,i),(c,j)] w[c][j]  for this rank's voxels (16-voxel z segments; needs zN % 16 == 0 and
+// c0 % 16 == 0).  K comes from the stationary tables: K[(r,i),(c,j)] = tab[c*3+r][C0 + L(j) - L(i)].
+// Block = 16 consecutive output segments x 4 z-quads x 4 groups of the contraction-column sweep.  A thread owns 4
+// consecutive outputs and slides a 4-entry window of the table along the contraction column (1 table load + 1/3 w load
+// per 4 FMAs).  The 16 segments of a block visit the contraction columns in a ROTATED order (cj = sweep index + own
+// column) so that at any moment they all need the SAME lattice offset, i.e. the same table stretch: the table loads of a
+// warp coalesce to one stretch and stay in L1 instead of each output column streaming all nine tables from L2.
 __global__ void __launch_bounds__(256) kw_kernel(const double* __restrict__ tables, long ext, long C0, int xN, int yN, int zN,
-                                                 const double* __restrict__ w, long Kp, long c0, double* __restrict__ z, long ncp) {
-    __shared__ double red[64][4][13];
-    const int tid = threadIdx.x, quad = tid & 3, g = tid >> 2;
-    const long i_base = c0 + (long)blockIdx.x * 16;
+                                                 const double* __restrict__ w, long Kp, long c0, long nseg, double* __restrict__ z,
+                                                 long ncp) {
+    __shared__ double red[4][64][13];
+    const int tid = threadIdx.x, quad = tid & 3, cl = (tid >> 2) & 15, dg = tid >> 6;
+    const long seg = (long)blockIdx.x * 16 + cl;
+    const bool live = seg < nseg;
+    const long i_base = c0 + (live ? seg : 0) * 16;
     const int ci = (int)(i_base / zN), iz0 = (int)(i_base % zN) + 4 * quad;
     const int lci = (ci / xN) * (2 * xN - 1) + ci % xN;
     const int ncolumns = xN * yN, zs = 2 * zN - 1;
+    // sweep range of this block (blockIdx.y of gridDim.y slices, for small shards) split over the 4 thread groups
+    const int slice = (ncolumns + gridDim.y - 1) / gridDim.y, sl0 = blockIdx.y * slice, sl1 = min(ncolumns, sl0 + slice);
+    const int per = (max(sl1 - sl0, 0) + 3) / 4, sw0 = sl0 + dg * per, sw1 = min(sl1, sw0 + per);
+    z += (long)blockIdx.y * 3 * ncp;
     double acc[3][4];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[r][q] = 0.0;
-    for (int cj = g; cj < ncolumns; cj += 64) {
+    for (int sw = sw0; sw < sw1; ++sw) {
+        int cj = sw + ci;
+        if (cj >= ncolumns) cj -= ncolumns;
         const int lcj = (cj / xN) * (2 * xN - 1) + cj % xN;
         const long base = C0 + (long)(lcj - lci) * zs - iz0;      // table offset of (jz = 0, this thread's first output)
         const double* wc = w + (long)cj * zN;
@@ -75,7 +87,7 @@ __global__ void __launch_bounds__(256) kw_kernel(const double* __restrict__ tabl
             const double* t0 = tables + (long)(c * 3 + 0) * ext + base;
             const double* t1 = tables + (long)(c * 3 + 1) * ext + base;
             const double* t2 = tables + (long)(c * 3 + 2) * ext + base;
-            // window: win[r][k] = table[jz - k]
+            // window: a_k = table[jz - k]
             double a1 = __ldg(t0 - 1), a2 = __ldg(t0 - 2), a3 = __ldg(t0 - 3);
             double b1 = __ldg(t1 - 1), b2 = __ldg(t1 - 2), b3 = __ldg(t1 - 3);
             double d1 = __ldg(t2 - 1), d2 = __ldg(t2 - 2), d3 = __ldg(t2 - 3);
@@ -95,13 +107,13 @@ __global__ void __launch_bounds__(256) kw_kernel(const double* __restrict__ tabl
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) red[g][quad][r * 4 + q] = acc[r][q];
+        for (int q = 0; q < 4; ++q) red[dg][tid & 63][r * 4 + q] = acc[r][q];
     __syncthreads();
-    if (tid < 48) {
-        const int r = tid / 16, o = tid % 16, qd = o >> 2, q = o & 3;
-        double s = 0.0;
-        for (int gg = 0; gg < 64; ++gg) s += red[gg][qd][r * 4 + q];      // fixed order: deterministic
-        z[(long)r * ncp + (long)blockIdx.x * 16 + o] = s;
+    for (int o = tid; o < 64 * 12; o += 256) {
+        const int lq = o / 12, rq = o % 12, r = rq >> 2, q = rq & 3;
+        const long sg = (long)blockIdx.x * 16 + (lq >> 2);
+        if (sg < nseg)      // fixed order over the four sweep groups: deterministic
+            z[(long)r * ncp + sg * 16 + (lq & 3) * 4 + q] = (red[0][lq][rq] + red[1][lq][rq]) + (red[2][lq][rq] + red[3][lq][rq]);
     }
 }
 
@@ -179,6 +191,15 @@ __global__ void __launch_bounds__(256) linv_t_gemv_kernel(const double* __restri
     }
 }
 
+// z[e] = sum over the sweep slices (fixed order)
+__global__ void kw_reduce_kernel(double* __restrict__ z, long count, int nslice) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    double s = z[e];
+    for (int k = 1; k < nslice; ++k) s += z[(long)k * count + e];
+    z[e] = s;
+}
+
 // out[0] = sum_m a[m] b[m]  (one block, fixed order)
 __global__ void dot_kernel(const double* __restrict__ a, const double* __restrict__ b, long n, double* __restrict__ out) {
     __shared__ double red[256];
@@ -208,8 +229,21 @@ cudaError_t refine_at_alpha(const RefineArgs& a, const double* alpha, double* w,
     return cudaGetLastError();
 }
 
+// sweep slices per output block so that small voxel-column shards (multi-GPU) still fill the SMs; z needs room for
+// refine_kw_slices(ncol) copies of [3][ncp]
+int refine_kw_slices(long ncol) {
+    const long nbx = (ncol / 16 + 15) / 16;
+    long k = (296 + nbx - 1) / (nbx > 0 ? nbx : 1);
+    return (int)(k < 1 ? 1 : (k > 8 ? 8 : k));
+}
+
 cudaError_t refine_kw(const RefineArgs& a, const double* w, double* z, cudaStream_t s) {
-    kw_kernel<<<(unsigned)(a.ncol / 16), 256, 0, s>>>(a.tables, a.ext, a.C0, a.n[0], a.n[1], a.n[2], w, a.Kp, a.c0, z, a.ncp);
+    const long nseg = a.ncol / 16;
+    const unsigned nbx = (unsigned)((nseg + 15) / 16);
+    const int nslice = refine_kw_slices(a.ncol);
+    dim3 grid(nbx, (unsigned)nslice);
+    kw_kernel<<<grid, 256, 0, s>>>(a.tables, a.ext, a.C0, a.n[0], a.n[1], a.n[2], w, a.Kp, a.c0, nseg, z, a.ncp);
+    if (nslice > 1) kw_reduce_kernel<<<(unsigned)((3 * a.ncp + 255) / 256), 256, 0, s>>>(z, 3 * a.ncp, nslice);
     return cudaGetLastError();
 }
 
