@@ -614,7 +614,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         if (p->a8_slices != S) {   // digit planes of the sensitivities: built once per problem and slice count
             for (int c = 0; c < 2; ++c) {
                 if (p->a8[c]) { gb_dev_free(ctx, p->a8[c]); p->a8[c] = nullptr; }
-                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a8[c], (size_t)ozaki_rows_bytes(Ns, p->Kp, S)));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a8[c], (size_t)ozaki_rows_bytes(Ns, p->Kp, S, ozaki_tile_np(S))));
                 if (!p->a_exp[c]) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a_exp[c], (size_t)Ns * sizeof(int)));
                 GB_CUDA(ctx, ozaki_slice_sens(p->A[c], Ns, p->N, p->lda, S, p->a_exp[c], p->a8[c], p->Kp, s));
             }
@@ -625,12 +625,12 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
             // (transposed digits of all of Pt): the two uses are sequential
             if (p->b8) { gb_dev_free(ctx, p->b8); p->b8 = nullptr; }
             if (p->b_exp) { gb_dev_free(ctx, p->b_exp); p->b_exp = nullptr; }
-            const size_t aka_bytes = 3 * (size_t)ozaki_rows_bytes(Ns, ncp, S, ozaki_tile_n(S));
+            const size_t aka_bytes = 3 * (size_t)ozaki_rows_bytes(Ns, ncp, S, 128);
             const size_t var_bytes = (size_t)ozaki_cols_bytes(ldp, Mp, S);
             p->b8_bytes = aka_bytes > var_bytes ? aka_bytes : var_bytes;
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->b8, p->b8_bytes));
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->b_exp, (size_t)(ldp > 3 * Ns ? ldp : 3 * Ns) * sizeof(int)));
-            p->bytes += 2 * (size_t)ozaki_rows_bytes(Ns, p->Kp, S) + p->b8_bytes;
+            p->bytes += 2 * (size_t)ozaki_rows_bytes(Ns, p->Kp, S, ozaki_tile_np(S)) + p->b8_bytes;
             p->a8_slices = S;
         }
         GB_CUDA(ctx, ozaki_slice_tables(p->tables, p->ext, S, p->t_exp, p->t8, s));
@@ -664,17 +664,18 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
 
     // ---- AkA = A3 . Pt^T (lower triangle) over this rank's voxel columns
     if (h->slices != 0) {
-        // int8 digit products: the sensitivities' digit blocks are reused (K steps c0/32 ..), the three Pt blocks
-        // (rows c', columns r = c) are sliced row-wise into N-side digit blocks
-        const int S = h->slices, NT = ozaki_tile_n(S);
-        const size_t blk = (size_t)ozaki_rows_bytes(Ns, ncp, S, NT);
+        // int8 digit products.  Block (c', c) of AkA: C[s'][s] = sum_j Pt[(c', s'), (c, j)] * A_c[s][j]: the Pt block is sliced
+        // row-wise into M-side digit blocks (128-row tiles), the sensitivities' N-side digit blocks of the projection are
+        // reused (K steps c0/32 ..).  Lower triangle: blocks (0,0) and (1,1) lower, (1,0) full.
+        const int S = h->slices;
+        const size_t blk = (size_t)ozaki_rows_bytes(Ns, ncp, S, 128);
         const int a_ksteps = (int)(p->Kp / 32), a_k0 = (int)(p->c0 / 32), ks = (int)(ncp / 32);
-        const int cc[3][2] = {{0, 0}, {1, 0}, {1, 1}};      // (c, c'): block row = A_c, block column = Pt rows of c'
+        const int cc[3][2] = {{0, 0}, {1, 0}, {1, 1}};      // (c', c): block row = Pt rows of c', block column = A_c
         for (int t = 0; t < 3; ++t) {
-            const int c = cc[t][0], cp_ = cc[t][1];
-            GB_CUDA(ctx, ozaki_slice_rows(p->Pt + (long)cp_ * Ns * ldp + (long)c * ncp, Ns, ncp, ldp, S, p->b_exp + t * Ns, p->b8 + t * blk, ncp, NT, s));
-            GB_CUDA(ctx, ozaki_gemm_store(p->a8[c], p->a_exp[c], a_ksteps, a_k0, p->b8 + t * blk, p->b_exp + t * Ns, ks, 0, ks, (int)Ns, (int)Ns,
-                                          p->Bm + (long)c * Ns * Mp + (long)cp_ * Ns, Mp, c == cp_ ? 1 : 0, S, ctx->sm_count, s));
+            const int cp_ = cc[t][0], c = cc[t][1];
+            GB_CUDA(ctx, ozaki_slice_rows(p->Pt + (long)cp_ * Ns * ldp + (long)c * ncp, Ns, ncp, ldp, S, p->b_exp + t * Ns, p->b8 + t * blk, ncp, 128, s));
+            GB_CUDA(ctx, ozaki_gemm_store(p->b8 + t * blk, p->b_exp + t * Ns, ks, 0, p->a8[c], p->a_exp[c], a_ksteps, a_k0, ks, (int)Ns, (int)Ns,
+                                          p->Bm + (long)cp_ * Ns * Mp + (long)c * Ns, Mp, c == cp_ ? 1 : 0, S, ctx->sm_count, s));
         }
         p->nlaunch += 8;
         if (p->nd) {
@@ -771,7 +772,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         }
         GB_CUDA(ctx, refine_scatter_mu(p->rf_z, ncp, ncol, p->mu, s));
         if (nref > 0) GB_CUDA(ctx, refine_dot(p->ydev, p->alpha, M, p->scal + 1, s));    // u.u = y^T (AkA)^-1 y with the refined alpha
-        GB_CUDA(ctx, ozaki_slice_sens(p->Linv, Mp, Mp, Mp, S, p->l_exp, p->l8, Mp, s));
+        GB_CUDA(ctx, ozaki_slice_rows(p->Linv, Mp, Mp, Mp, S, p->l_exp, p->l8, Mp, 128, s));
         GB_CUDA(ctx, ozaki_slice_cols_mean(p->Pt, Mp, ldp, ldp, S, p->b_exp, p->b8, p->alpha, nullptr, ncp, ncol, s));
         GB_CUDA(ctx, ozaki_colsumsq_tri(p->l8, p->l_exp, p->b8, p->b_exp, (int)Mp, ldp, S, p->partial, p->vscratch, ctx->sm_count, s));
         GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));

@@ -142,6 +142,7 @@ struct OzakiArgs {
     int Ns, ncol, c0;
 };
 int ozaki_tile_n(int slices);
+int ozaki_tile_np(int slices);
 int ozaki_chunk();
 long ozaki_table_bytes(long ext, int slices);
 long ozaki_rows_bytes(long rows, long kp, int slices, int tr = 128);

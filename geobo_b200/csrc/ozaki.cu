@@ -111,7 +111,7 @@ __global__ void slice_table_kernel(const double* __restrict__ tab, long ext, con
 
 // ------------------------------------------------------------------------------------------------ main kernel
 struct Params {
-    const uint8_t* a8[2];     // pre-tiled digit blocks of A_grav / A_magn: [row tile][k step][digit][4096]
+    const uint8_t* a8[2];     // pre-tiled digit blocks of A_grav / A_magn, N-side layout: [row tile of NT][k step][digit][NT*32]
     const int* a_exp[2];      // [Ns]
     const uint8_t* t8;        // [9][S][plane_stride(ext)] digit planes of the covariance tables (only c = 0, 1 are used)
     const int* t_exp;         // [9]
@@ -119,26 +119,40 @@ struct Params {
     double* Pt;               // [Mp][ldp]
     long ext, C0, kp, ldp, ncp;
     int Ns, ncol, c0, chunk;  // chunk: contraction indices per accumulator flush (multiple of 32)
-    int n_stile, n_itile;
+    int n_stile, n_itile;     // sensor-row tiles of NT, voxel-column tiles of 128
 };
 
+constexpr int PROD_SLOTS = 3;                          // producer warps per TMEM lane quarter
+constexpr int TS_THREADS = (6 + 4 * PROD_SLOTS) * 32;  // 4 epilogue + MMA + copy + 12 producer warps
+// shared-memory ring of the sensitivity digits: the stages are small (S * NT * 32 B) and a bulk copy takes a few thousand
+// clocks end to end, so the ring is as deep as shared memory allows (<= 32 stages, <= 200 KB)
+template <int S> __host__ __device__ constexpr int ring_stages() { return (200 * 1024) / (S * Cfg<S>::NTP * 32) < 32 ? (200 * 1024) / (S * Cfg<S>::NTP * 32) : 32; }
+
+// Tile = 128 voxel columns (M side) x NT sensor rows (N side); D[m][n] = sum_j K[(c,j),(r,i0+m)] * A_c[s0+n][j].
+//   * M-side operand = covariance digits, GENERATED by the producer warps straight into TENSOR MEMORY (tcgen05.st; the MMA
+//     reads its A operand from TMEM, so it costs no shared-memory bandwidth and no small-N penalty);
+//   * N-side operand = sensitivity digits, one bulk async copy per K step into an 8-deep shared-memory ring;
+//   * accumulators: S levels x NT columns of TMEM; 2 x S x 8 columns hold the double-buffered A digits.
 template <int S>
-__global__ void __launch_bounds__((5 + Cfg<S>::W) * 32, 1) ozaki_project_kernel(const __grid_constant__ Params P) {
-    constexpr int NT = Cfg<S>::NT, W = Cfg<S>::W, STAGES = Cfg<S>::STAGES, NSEG = NT / 16;
-    constexpr int A_BYTES = S * 4096, B_SLICE = NT * 32, STAGE_BYTES = A_BYTES + S * B_SLICE;
-    constexpr int TMEM_COLS = 512;
-    constexpr int G = 256 / NT;          // B digits per MMA instruction (N <= 256)
-    static_assert(S * NT <= TMEM_COLS, "accumulators do not fit in TMEM");
-    static_assert(STAGES % W == 0, "a producer warp must own its stages");
+__global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __grid_constant__ Params P) {
+    constexpr int NT = Cfg<S>::NTP, SB = ring_stages<S>();
+    constexpr int B_SLICE = NT * 32, B_BYTES = S * B_SLICE;
+    constexpr int TMEM_COLS = 512, ACC = S * NT, ABUF = 8 * S;
+    constexpr int G = (256 / NT) < S ? (256 / NT) : S;          // B digit planes per MMA instruction (N <= 256)
+    static_assert(ACC + NABUF * ABUF <= TMEM_COLS, "accumulators + A digit buffers do not fit in TMEM");
+    static_assert(SB >= 2 * NABUF, "ring must be deeper than the A buffers (barrier parities stay unambiguous)");
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar, tempty_bar;
+    // one full / done barrier pair per ring slot (slot = it % SB): `full` collects the four producer warps of the step and the
+    // bytes of the sensitivity-digit bulk copy, `done` is signalled by ONE tcgen05.commit per step and releases both the
+    // TMEM A buffer (to the producers of step it + NABUF) and the shared-memory stage (to the copy of step it + SB)
+    __shared__ uint64_t full_bar[SB], done_bar[SB], tfull_bar, tempty_bar;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 4) {
         tmem_alloc(&tmem_base_s, TMEM_COLS);
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < SB; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&done_bar[s], 1); }
             mbar_init(&tfull_bar, 1);
             mbar_init(&tempty_bar, 128);
             fence_barrier_init();
@@ -154,124 +168,165 @@ __global__ void __launch_bounds__((5 + Cfg<S>::W) * 32, 1) ozaki_project_kernel(
     const int ksteps = (int)(P.kp / 32);
     const int chunk_steps = P.chunk / 32;
 
-    if (warp >= 5) {
-        // =============================================================== producers (one warp per stage)
-        const int w = warp - 5;
-        const int n = lane & 15, kh = lane >> 4;      // lane <-> (column within a 16-column segment, 16-byte K half)
+    if (warp >= 6) {
+        // =============================================================== covariance-digit producers -> TMEM
+        // warp <-> (TMEM lane quarter q = warp % 4, slot sl): handles the K steps with it % PROD_SLOTS == sl for rows 32 q ..
+        const int q4 = warp & 3, sl = (warp - 6) >> 2;
+        const int n = lane & 15;                       // column inside the 16-column segment of this half-warp
         const long plane = plane_stride(P.ext);
         const int C0 = (int)P.C0;
         uint32_t it_tile0 = 0;
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it_tile0 += (uint32_t)ksteps) {
             const int task = (int)(tile / tiles_per_task);            // c * 3 + r
-            const long rem = tile % tiles_per_task;
-            const int stile = (int)(rem / P.n_itile), itile = (int)(rem % P.n_itile);
-            const int c = task / 3;
-            const int i0 = itile * NT;
-            const uint8_t* a_src = P.a8[c] + (size_t)stile * ksteps * A_BYTES;
+            const int itile = (int)((tile % tiles_per_task) % P.n_itile);
+            const int i0 = itile * 128 + 32 * q4 + (lane & 16);       // first voxel column of this half-warp's segment
             const uint8_t* t8 = P.t8 + (size_t)task * S * plane;
-            int li_reg = 0;                                // lattice id of the first column of segment `lane`
-            if (lane < NSEG) li_reg = P.L[P.c0 + min(i0 + lane * 16, P.ncol - 16)];
-            int ks = (int)((uint32_t)(w + W - (int)(it_tile0 % W)) % W);
-            int lj_next = ks < ksteps ? P.L[ks * 32 + kh * 16] : 0;
-            for (; ks < ksteps; ks += W) {
-                const uint32_t it = it_tile0 + (uint32_t)ks;
-                const int st = (int)(it % STAGES);
-                const int lj = lj_next;
-                if (ks + W < ksteps) lj_next = P.L[(ks + W) * 32 + kh * 16];
-                mbar_wait(&empty_bar[st], ((it / STAGES) & 1) ^ 1);
-                uint8_t* sa = smem + st * STAGE_BYTES;
-                uint8_t* sb = sa + A_BYTES;
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full_bar[st], A_BYTES);
-                    bulk_g2s(sa, a_src + (size_t)ks * A_BYTES, A_BYTES, &full_bar[st]);
-                }
-                // ---- K digits, phase 1: every half-warp loads the aligned words covering its 31-byte table stretch
-                uint32_t word[NSEG][S];
-                int wi[NSEG];
-                uint32_t sh[NSEG];
+            const int lseg = P.L[P.c0 + min(i0, P.ncol - 16)];
+            int ks = (int)((uint32_t)(sl + PROD_SLOTS - (int)(it_tile0 % PROD_SLOTS)) % PROD_SLOTS);
+            // software pipeline over this warp's K steps: the lattice ids are loaded two own steps ahead, the table words one
+            // own step ahead, the digit windows are assembled in registers BEFORE waiting for the TMEM buffer, so that only the
+            // five tcgen05.st sit between "MMAs of step it-2 done" and "A digits of step it ready"
+            int lj_nn[2];                                  // lattice ids of step ks + PROD_SLOTS
+            uint32_t word[2][S];                           // table words of step ks
+            int wi[2];
+            uint32_t sh[2];
+            auto load_lj = [&](int k, int (&lj)[2]) {
+                const int kk = min(k, ksteps - 1);
+                lj[0] = P.L[kk * 32];
+                lj[1] = P.L[kk * 32 + 16];
+            };
+            auto load_words = [&](const int (&lj)[2]) {
 #pragma unroll
-                for (int sg = 0; sg < NSEG; ++sg) {
-                    const int li = __shfl_sync(0xffffffffu, li_reg, sg);
-                    const int offmin = C0 + lj - li - 15;          // table offset of (i = segment start + 15, j = half start); symmetric table
-                    const int d = (offmin & 3) + 15 - n;           // this lane's window starts d bytes after the aligned base
-                    wi[sg] = d >> 2;
-                    sh[sg] = (uint32_t)(d & 3) * 8;
+                for (int kh = 0; kh < 2; ++kh) {
+                    const int offmin = C0 + lj[kh] - lseg - 15;       // table offset of (column n = 15, first j of the half); symmetric table
+                    const int d = (offmin & 3) + 15 - n;              // this lane's window starts d bytes after the aligned base
+                    wi[kh] = d >> 2;
+                    sh[kh] = (uint32_t)(d & 3) * 8;
                     const uint8_t* src = t8 + (offmin & ~3) + 4 * n;
 #pragma unroll
-                    for (int q = 0; q < S; ++q) word[sg][q] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)q * plane));
+                    for (int q = 0; q < S; ++q) word[kh][q] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)q * plane));
                 }
-                // ---- phase 2: pick the unaligned 16-byte window (5 words) and store it in canonical layout
+            };
+            {
+                int lj0[2];
+                load_lj(ks, lj0);
+                load_lj(ks + PROD_SLOTS, lj_nn);
+                load_words(lj0);
+            }
+            for (; ks < ksteps; ks += PROD_SLOTS) {
+                const uint32_t it = it_tile0 + (uint32_t)ks;
+                // ---- assemble the unaligned 16-byte windows of this step: v[q][0..3] = K half 0, v[q][4..7] = K half 1
+                uint32_t v[S][8];
 #pragma unroll
-                for (int sg = 0; sg < NSEG; ++sg) {
-                    const int src_lane = (lane & 16) + wi[sg];
+                for (int q = 0; q < S; ++q) {
 #pragma unroll
-                    for (int q = 0; q < S; ++q) {
-                        const uint32_t w0 = __shfl_sync(0xffffffffu, word[sg][q], src_lane);
-                        const uint32_t w1 = __shfl_sync(0xffffffffu, word[sg][q], src_lane + 1);
-                        const uint32_t w2 = __shfl_sync(0xffffffffu, word[sg][q], src_lane + 2);
-                        const uint32_t w3 = __shfl_sync(0xffffffffu, word[sg][q], src_lane + 3);
-                        const uint32_t w4 = __shfl_sync(0xffffffffu, word[sg][q], src_lane + 4);
-                        uint4 v;
-                        v.x = __funnelshift_r(w0, w1, sh[sg]);
-                        v.y = __funnelshift_r(w1, w2, sh[sg]);
-                        v.z = __funnelshift_r(w2, w3, sh[sg]);
-                        v.w = __funnelshift_r(w3, w4, sh[sg]);
-                        *reinterpret_cast<uint4*>(sb + q * B_SLICE + core_offset(sg * 16 + n, kh)) = v;
+                    for (int kh = 0; kh < 2; ++kh) {
+                        const int src_lane = (lane & 16) + wi[kh];
+                        const uint32_t w0 = __shfl_sync(0xffffffffu, word[kh][q], src_lane);
+                        const uint32_t w1 = __shfl_sync(0xffffffffu, word[kh][q], src_lane + 1);
+                        const uint32_t w2 = __shfl_sync(0xffffffffu, word[kh][q], src_lane + 2);
+                        const uint32_t w3 = __shfl_sync(0xffffffffu, word[kh][q], src_lane + 3);
+                        const uint32_t w4 = __shfl_sync(0xffffffffu, word[kh][q], src_lane + 4);
+                        v[q][4 * kh + 0] = __funnelshift_r(w0, w1, sh[kh]);
+                        v[q][4 * kh + 1] = __funnelshift_r(w1, w2, sh[kh]);
+                        v[q][4 * kh + 2] = __funnelshift_r(w2, w3, sh[kh]);
+                        v[q][4 * kh + 3] = __funnelshift_r(w3, w4, sh[kh]);
                     }
                 }
-                fence_proxy_async_smem();
+                // ---- prefetch: table words of the next own step, lattice ids of the one after
+                {
+                    int ljn[2] = {lj_nn[0], lj_nn[1]};
+                    load_lj(ks + 2 * PROD_SLOTS, lj_nn);
+                    load_words(ljn);
+                }
+                // ---- the TMEM buffer (it % NABUF) is free once the MMAs of step it - NABUF have completed
+                if (it >= NABUF) mbar_wait(&done_bar[(it - NABUF) % SB], ((it - NABUF) / SB) & 1);
+                tc_fence_after();
+                const uint32_t abuf = tmem_base + ((uint32_t)(32 * q4) << 16) + ACC + (it % NABUF) * ABUF;
+#pragma unroll
+                for (int q = 0; q < S; ++q) tmem_st8(abuf + 8 * q, v[q]);
+                tmem_st_wait();
+                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[st]);
+                if (lane == 0) mbar_arrive(&full_bar[it % SB]);
+            }
+        }
+    } else if (warp == 5) {
+        // =============================================================== sensitivity-digit copies (one elected lane)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int task = (int)(tile / tiles_per_task);
+                const int stile = (int)((tile % tiles_per_task) / P.n_itile);
+                const uint8_t* src = P.a8[task / 3] + (size_t)stile * ksteps * B_BYTES;
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int st = (int)(it % SB);
+                    mbar_wait(&done_bar[st], ((it / SB) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[st], B_BYTES);
+                    bulk_g2s(smem + st * B_BYTES, src + (size_t)ks * B_BYTES, B_BYTES, &full_bar[st]);
+                }
             }
         }
     } else if (warp == 4) {
-        // =============================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            uint32_t it = 0, chunk_id = 0;
+        // =============================================================== MMA issuer: the whole warp runs the (uniform) loop,
+        // one elected lane issues the tcgen05 instructions
+        {
+            uint32_t chunk_id = 0;
+            // running ring state (no div / mod / multiplies in the issue loop): ring slot, its barrier addresses and phase,
+            // the low word of the B descriptor (address >> 4) and the TMEM address of the A buffer
+            int rp = 0, ab = 0;
+            uint32_t ph = 0;
+            const uint64_t bdesc0 = smem_desc(smem_u32(smem), kLBO, kSBO);
+            uint64_t bdesc = bdesc0;
+            uint32_t at = tmem_base + ACC;
+            uint64_t* fb = full_bar;
+            uint64_t* db = done_bar;
             for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int k0 = 0; k0 < ksteps; k0 += chunk_steps, ++chunk_id) {
                     const int k1 = min(ksteps, k0 + chunk_steps);
                     mbar_wait(&tempty_bar, (chunk_id & 1) ^ 1);     // epilogue has drained the accumulators
                     tc_fence_after();
-                    for (int ks = k0; ks < k1; ++ks, ++it) {
-                        const int st = (int)(it % STAGES);
-                        mbar_wait(&full_bar[st], (it / STAGES) & 1);
+                    for (int ks = k0; ks < k1; ++ks) {
+                        mbar_wait(fb, ph);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + st * STAGE_BYTES), sb = sa + A_BYTES;
                         const uint32_t acc = ks == k0 ? 0u : 1u;
-                        // A digit qa times B digits qb0 .. qb0+g-1 in ONE instruction of N = g * NT columns: the B digit
-                        // planes are consecutive rows of the canonical layout and product (qa, qb) lands in the
-                        // accumulator of level qa + qb at column (qa + qb) * NT.
+                        if (elect_one()) {
+                        // covariance digit qa (TMEM) times sensitivity digits qb0 .. qb0+g-1 (consecutive planes of the canonical
+                        // layout) in ONE instruction of N = g * NT columns; product (qa, qb) lands in level qa + qb
 #pragma unroll
                         for (int qa = 0; qa < S; ++qa) {
-                            const uint64_t ad = smem_desc(sa + qa * 4096, kLBO, kSBO);
 #pragma unroll
                             for (int qb0 = 0; qb0 < S - qa; qb0 += G) {
                                 const int g = (S - qa - qb0) < G ? (S - qa - qb0) : G;
-                                const uint64_t bd = smem_desc(sb + qb0 * B_SLICE, kLBO, kSBO);
-                                mma_i8(tmem_base + (qa + qb0) * NT, ad, bd, idesc_i8(1, 1, g * NT), qa == 0 ? acc : 1u);
+                                mma_i8_ts(tmem_base + (qa + qb0) * NT, at + 8 * qa, bdesc + (uint64_t)((qb0 * B_SLICE) >> 4), idesc_i8(1, 1, g * NT),
+                                          qa == 0 ? acc : 1u);
                             }
                         }
-                        mma_commit(&empty_bar[st]);       // stage reusable once these MMAs have read it
+                        mma_commit(db);                   // TMEM A buffer and shared-memory stage reusable once these MMAs have read them
+                        }
+                        ++fb; ++db; bdesc += (uint64_t)(B_BYTES >> 4); at += ABUF;
+                        if (++rp == SB) { rp = 0; ph ^= 1; fb = full_bar; db = done_bar; bdesc = bdesc0; }
+                        if (++ab == NABUF) { ab = 0; at = tmem_base + ACC; }
                     }
-                    mma_commit(&tfull_bar);               // accumulators of this chunk complete
+                    if (elect_one()) mma_commit(&tfull_bar);               // accumulators of this chunk complete
                 }
             }
         }
     } else {
         // =============================================================== epilogue (warps 0-3 <-> TMEM lanes 32 w .. 32 w + 31)
         uint32_t chunk_id = 0;
-        const int row = warp * 32 + lane;
+        const int m = warp * 32 + lane;                   // row of D = voxel column inside the tile
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int task = (int)(tile / tiles_per_task);
             const long rem = tile % tiles_per_task;
             const int stile = (int)(rem / P.n_itile), itile = (int)(rem % P.n_itile);
             const int c = task / 3, r = task % 3;
-            const int s = stile * 128 + row, i0 = itile * NT;
-            const bool row_ok = s < P.Ns;
+            const int s0 = stile * NT, i = itile * 128 + m;
+            const bool col_ok = i < P.ncol;
             // result = 2^(eA + eK - 14 - 8 (S-1)) * sum_l acc_l 2^(8 (S-1-l))
-            const double scale = row_ok ? ldexp(1.0, P.a_exp[c][s] + P.t_exp[task] - 14 - 8 * (S - 1)) : 0.0;
-            double* prow = P.Pt + ((long)c * P.Ns + (row_ok ? s : 0)) * P.ldp + (long)r * P.ncp + i0;
+            const int ebase = P.t_exp[task] - 14 - 8 * (S - 1);
+            const int* aexp = P.a_exp[c];
+            double* pcol = P.Pt + ((long)c * P.Ns + s0) * P.ldp + (long)r * P.ncp + (col_ok ? i : 0);
             for (int k0 = 0; k0 < ksteps; k0 += chunk_steps, ++chunk_id) {
                 mbar_wait(&tfull_bar, chunk_id & 1);
                 tc_fence_after();
@@ -280,16 +335,17 @@ __global__ void __launch_bounds__((5 + Cfg<S>::W) * 32, 1) ozaki_project_kernel(
 #pragma unroll
                     for (int lvl = 0; lvl < S; ++lvl) tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + lvl * NT + n0, v[lvl]);
                     tmem_ld_wait();
-                    if (row_ok) {
+                    if (col_ok) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            long long acc = (long long)(int)v[0][k];
+                            const int s = s0 + n0 + k;
+                            if (s < P.Ns) {
+                                long long acc = (long long)(int)v[0][k];
 #pragma unroll
-                            for (int lvl = 1; lvl < S; ++lvl) acc = acc * 256 + (long long)(int)v[lvl][k];
-                            const int col = i0 + n0 + k;
-                            if (col < P.ncol) {
-                                const double add = scale * (double)acc;
-                                prow[n0 + k] = (k0 == 0) ? add : prow[n0 + k] + add;
+                                for (int lvl = 1; lvl < S; ++lvl) acc = acc * 256 + (long long)(int)v[lvl][k];
+                                const double add = ldexp((double)acc, aexp[s] + ebase);
+                                double* dst = pcol + (long)(n0 + k) * P.ldp;          // 32 lanes -> 32 consecutive doubles of one Pt row
+                                *dst = (k0 == 0) ? add : *dst + add;
                             }
                         }
                     }
@@ -306,15 +362,16 @@ __global__ void __launch_bounds__((5 + Cfg<S>::W) * 32, 1) ozaki_project_kernel(
 
 template <int S>
 static cudaError_t launch_one(const Params& P, int sm_count, cudaStream_t s) {
-    constexpr int NT = Cfg<S>::NT;
-    constexpr int smem = Cfg<S>::STAGES * (S * 4096 + S * NT * 32);
+    constexpr int NT = Cfg<S>::NTP;
+    constexpr int smem = ring_stages<S>() * S * NT * 32;
     cudaError_t e = cudaFuncSetAttribute(ozaki_project_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     Params q = P;
-    q.n_itile = (P.ncol + NT - 1) / NT;
+    q.n_stile = (P.Ns + NT - 1) / NT;
+    q.n_itile = (P.ncol + 127) / 128;
     const long ntiles = 6L * q.n_stile * q.n_itile;
     const int grid = (int)(ntiles < (long)sm_count ? ntiles : (long)sm_count);
-    ozaki_project_kernel<S><<<grid, (5 + Cfg<S>::W) * 32, smem, s>>>(q);
+    ozaki_project_kernel<S><<<grid, TS_THREADS, smem, s>>>(q);
     return cudaGetLastError();
 }
 
@@ -338,6 +395,8 @@ int ozaki_chunk() {
 }
 
 int ozaki_tile_n(int slices) { return slices == 4 ? ozaki::Cfg<4>::NT : slices == 5 ? ozaki::Cfg<5>::NT : slices == 6 ? ozaki::Cfg<6>::NT : 0; }
+// row-tile size of the sensitivities' digit blocks (N-side operand of the projection and of the AkA products)
+int ozaki_tile_np(int slices) { return slices == 4 ? ozaki::Cfg<4>::NTP : slices == 5 ? ozaki::Cfg<5>::NTP : slices == 6 ? ozaki::Cfg<6>::NTP : 0; }
 
 // bytes of the pre-tiled digit blocks of a rows x kp operand with `tr` rows per tile (128: M side, tile_n: N side)
 long ozaki_rows_bytes(long rows, long kp, int slices, int tr) { return ((rows + tr - 1) / tr) * (kp / 32) * (long)slices * tr * 32; }
@@ -355,8 +414,9 @@ cudaError_t ozaki_slice_rows(const double* A, long rows, long cols, long ld, int
     return cudaGetLastError();
 }
 
+// sensitivities: N-side operand of the projection (tiles of ozaki_tile_n rows)
 cudaError_t ozaki_slice_sens(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp, cudaStream_t s) {
-    return ozaki_slice_rows(A, rows, cols, ld, slices, exps, out, kp, 128, s);
+    return ozaki_slice_rows(A, rows, cols, ld, slices, exps, out, kp, ozaki_tile_np(slices), s);
 }
 
 cudaError_t ozaki_slice_tables(const double* tables, long ext, int slices, int* exps, uint8_t* out, cudaStream_t s) {
@@ -380,7 +440,7 @@ cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStre
     P.ext = a.ext; P.C0 = a.C0; P.kp = a.kp; P.ldp = a.ldp; P.ncp = a.ncp;
     P.Ns = a.Ns; P.ncol = a.ncol; P.c0 = a.c0;
     P.chunk = ozaki_chunk();
-    P.n_stile = (a.Ns + 127) / 128;
+    P.n_stile = 0;
     P.n_itile = 0;
     switch (slices) {
         case 4: return ozaki::launch_one<4>(P, sm_count, s);

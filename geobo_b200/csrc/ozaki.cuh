@@ -10,12 +10,16 @@ namespace ozaki {
 constexpr int TABLE_PAD = 64;
 __host__ __device__ constexpr long plane_stride(long ext) { return (ext + TABLE_PAD + 15) & ~15L; }   // keeps every digit plane 16-byte aligned
 
-// Tile shape per slice count: the S accumulators of one 128 x NT tile fill TMEM (S * NT <= 512 columns);
-// W producer warps, STAGES (multiple of W) shared-memory stages of S * (4096 + NT * 32) bytes.
+// Tile shapes per slice count S.  Every kernel keeps S int32 accumulators (one per significance level) of NT TMEM columns.
+//   * projection (ozaki.cu, A operand generated into tensor memory): NTP sensor rows per tile; the A digits need
+//     NABUF x S x 8 TMEM columns (NABUF-deep: the commit -> producer -> tcgen05.st -> MMA hand-off latency is ~3 K steps),
+//     S * NTP + NABUF * 8 * S <= 512.  NTP is also the row-tile size of the sensitivities' digit blocks in memory.
+//   * GEMM with both operands in shared memory (ozaki_gemm.cu): NT output columns, S * NT <= 512, STAGES-deep ring.
 template <int S> struct Cfg;
-template <> struct Cfg<4> { static constexpr int NT = 128, W = 6, STAGES = 6; };
-template <> struct Cfg<5> { static constexpr int NT = 96, W = 6, STAGES = 6; };
-template <> struct Cfg<6> { static constexpr int NT = 80, W = 5, STAGES = 5; };
+template <> struct Cfg<4> { static constexpr int NT = 128, NTP = 112, STAGES = 6; };
+template <> struct Cfg<5> { static constexpr int NT = 96, NTP = 80, STAGES = 6; };
+template <> struct Cfg<6> { static constexpr int NT = 80, NTP = 64, STAGES = 5; };
+constexpr int NABUF = 2;
 
 // ------------------------------------------------------------------------------------------------ digit extraction
 // t in [-1/2, 1/2]: BALANCED digits (every d_q in [-128, 127], stored as two's-complement bytes) of t rounded to

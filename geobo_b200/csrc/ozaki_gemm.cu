@@ -147,12 +147,13 @@ __device__ __forceinline__ bool tile_coords(const GemmParams& P, long tile, int&
     return !(P.lower && (long)nt * NT > (long)mt * 128 + 127);
 }
 
-template <int S, int EPI>
+template <int S, int NT, int EPI>
 __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(const __grid_constant__ GemmParams P) {
-    constexpr int NT = Cfg<S>::NT, STAGES = Cfg<S>::STAGES;
+    constexpr int STAGES = Cfg<S>::STAGES;
     constexpr int A_BYTES = S * 4096, B_SLICE = NT * 32, B_BYTES = S * B_SLICE, STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = 512;
-    constexpr int G = 256 / NT;
+    constexpr int G = (256 / NT) < S ? (256 / NT) : S;
+    static_assert(S * NT <= TMEM_COLS, "accumulators do not fit in TMEM");
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar, tempty_bar;
     __shared__ uint32_t tmem_base_s;
@@ -195,9 +196,15 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(const __grid_constan
             }
         }
     } else if (warp == 4) {
-        // =============================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            uint32_t it = 0, chunk_id = 0;
+        // =============================================================== MMA issuer: the whole warp runs the (uniform) loop with
+        // running ring state (no div / mod / descriptor rebuilds per step), one elected lane issues the tcgen05 instructions
+        {
+            uint32_t chunk_id = 0, ph = 0;
+            int st = 0;
+            const uint64_t adesc0 = smem_desc(smem_u32(smem), kLBO, kSBO);
+            uint64_t adesc = adesc0;
+            uint64_t* fb = full_bar;
+            uint64_t* eb = empty_bar;
             for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 int mt, nt;
                 if (!tile_coords<NT>(P, tile, mt, nt)) continue;
@@ -206,25 +213,26 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(const __grid_constan
                     const int k1 = min(kend, k0 + P.chunk_steps);
                     mbar_wait(&tempty_bar, (chunk_id & 1) ^ 1);
                     tc_fence_after();
-                    for (int ks = k0; ks < k1; ++ks, ++it) {
-                        const int st = (int)(it % STAGES);
-                        mbar_wait(&full_bar[st], (it / STAGES) & 1);
+                    for (int ks = k0; ks < k1; ++ks) {
+                        mbar_wait(fb, ph);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + st * STAGE_BYTES), sb = sa + A_BYTES;
                         const uint32_t acc = ks == k0 ? 0u : 1u;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int qa = 0; qa < S; ++qa) {
-                            const uint64_t ad = smem_desc(sa + qa * 4096, kLBO, kSBO);
+                            for (int qa = 0; qa < S; ++qa) {
 #pragma unroll
-                            for (int qb0 = 0; qb0 < S - qa; qb0 += G) {
-                                const int g = (S - qa - qb0) < G ? (S - qa - qb0) : G;
-                                const uint64_t bd = smem_desc(sb + qb0 * B_SLICE, kLBO, kSBO);
-                                mma_i8(tmem_base + (qa + qb0) * NT, ad, bd, idesc_i8(1, 1, g * NT), qa == 0 ? acc : 1u);
+                                for (int qb0 = 0; qb0 < S - qa; qb0 += G) {
+                                    const int g = (S - qa - qb0) < G ? (S - qa - qb0) : G;
+                                    mma_i8(tmem_base + (qa + qb0) * NT, adesc + (uint64_t)((qa * 4096) >> 4),
+                                           adesc + (uint64_t)((A_BYTES + qb0 * B_SLICE) >> 4), idesc_i8(1, 1, g * NT), qa == 0 ? acc : 1u);
+                                }
                             }
+                            mma_commit(eb);
                         }
-                        mma_commit(&empty_bar[st]);
+                        ++fb; ++eb; adesc += (uint64_t)(STAGE_BYTES >> 4);
+                        if (++st == STAGES) { st = 0; ph ^= 1; fb = full_bar; eb = empty_bar; adesc = adesc0; }
                     }
-                    mma_commit(&tfull_bar);
+                    if (elect_one()) mma_commit(&tfull_bar);
                 }
             }
         }
@@ -301,11 +309,10 @@ __global__ void __launch_bounds__(192, 1) ozaki_gemm_kernel(const __grid_constan
     if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int S, int EPI>
+template <int S, int NT, int EPI>
 static cudaError_t launch_gemm(GemmParams P, int sm_count, cudaStream_t s) {
-    constexpr int NT = Cfg<S>::NT;
     constexpr int smem = Cfg<S>::STAGES * (S * 4096 + S * NT * 32);
-    cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<S, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     P.n_mtile = (P.M + 127) / 128;
     P.n_ntile = (P.N + NT - 1) / NT;
@@ -315,7 +322,7 @@ static cudaError_t launch_gemm(GemmParams P, int sm_count, cudaStream_t s) {
     P.gm = (int)(gm < 1 ? 1 : (gm > P.n_mtile ? P.n_mtile : gm));
     const long ntiles = (long)P.n_mtile * P.n_ntile;
     const int grid = (int)(ntiles < (long)sm_count ? ntiles : (long)sm_count);
-    ozaki_gemm_kernel<S, EPI><<<grid, 192, smem, s>>>(P);
+    ozaki_gemm_kernel<S, NT, EPI><<<grid, 192, smem, s>>>(P);
     return cudaGetLastError();
 }
 
@@ -360,14 +367,15 @@ cudaError_t ozaki_colsumsq_tri(const uint8_t* a8, const int* a_exp, const uint8_
     if (P.ksteps > P.chunk_steps && !scratch) return cudaErrorInvalidValue;
     P.tri = 1;
     switch (slices) {
-        case 4: return ozaki::launch_gemm<4, ozaki::EPI_SUMSQ>(P, sm_count, s);
-        case 5: return ozaki::launch_gemm<5, ozaki::EPI_SUMSQ>(P, sm_count, s);
-        case 6: return ozaki::launch_gemm<6, ozaki::EPI_SUMSQ>(P, sm_count, s);
+        case 4: return ozaki::launch_gemm<4, ozaki::Cfg<4>::NT, ozaki::EPI_SUMSQ>(P, sm_count, s);
+        case 5: return ozaki::launch_gemm<5, ozaki::Cfg<5>::NT, ozaki::EPI_SUMSQ>(P, sm_count, s);
+        case 6: return ozaki::launch_gemm<6, ozaki::Cfg<6>::NT, ozaki::EPI_SUMSQ>(P, sm_count, s);
     }
     return cudaErrorInvalidValue;
 }
 
-// C[m, n] = sum_k A[m, k] B[n, k] over K steps [a_k0, a_k0 + ksteps) of A and [b_k0, ...) of B; lower: skip tiles above the diagonal
+// C[m, n] = sum_k A[m, k] B[n, k] over K steps [a_k0, a_k0 + ksteps) of A and [b_k0, ...) of B; lower: skip tiles above the diagonal.
+// The B operand is tiled in rows of ozaki_tile_np(slices) (the sensitivities' digit blocks of the projection are reused).
 cudaError_t ozaki_gemm_store(const uint8_t* a8, const int* a_exp, int a_ksteps, int a_k0, const uint8_t* b8, const int* b_exp, int b_ksteps,
                              int b_k0, int ksteps, int M, int N, double* C, long ldc, int lower, int slices, int sm_count, cudaStream_t s) {
     ozaki::GemmParams P;
@@ -377,9 +385,9 @@ cudaError_t ozaki_gemm_store(const uint8_t* a8, const int* a_exp, int a_ksteps, 
     P.chunk_steps = ozaki_chunk() / 32;
     P.lower = lower;
     switch (slices) {
-        case 4: return ozaki::launch_gemm<4, ozaki::EPI_STORE>(P, sm_count, s);
-        case 5: return ozaki::launch_gemm<5, ozaki::EPI_STORE>(P, sm_count, s);
-        case 6: return ozaki::launch_gemm<6, ozaki::EPI_STORE>(P, sm_count, s);
+        case 4: return ozaki::launch_gemm<4, ozaki::Cfg<4>::NTP, ozaki::EPI_STORE>(P, sm_count, s);
+        case 5: return ozaki::launch_gemm<5, ozaki::Cfg<5>::NTP, ozaki::EPI_STORE>(P, sm_count, s);
+        case 6: return ozaki::launch_gemm<6, ozaki::Cfg<6>::NTP, ozaki::EPI_STORE>(P, sm_count, s);
     }
     return cudaErrorInvalidValue;
 }

@@ -31,6 +31,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (mbarrier.test_wait): no hardware suspend, for latency-critical hand-offs
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 30); ++spin)
+        if (mbar_test_wait(bar, parity)) return;
+    __trap();
+}
 // Bounded wait: a protocol bug must never hang the GPU -- trap instead (kills only this context).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0; spin < (1u << 28); ++spin)
@@ -50,6 +67,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy writes (st.shared / cp.async) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// one lane of a CONVERGED warp: the warp keeps executing the surrounding (uniform) code together, only the tcgen05 issue is
+// predicated on the elected lane -- descriptors then live in uniform registers and the compiler needs no per-lane
+// "waterfall" loop around every UTCIMMA
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // ---- TMEM allocation (one warp, .sync.aligned)
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

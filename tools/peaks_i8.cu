@@ -105,23 +105,23 @@ __global__ void __launch_bounds__(160, 1) i8_rate_unrolled(int iters, long long*
 
 // A operand from tensor memory (TS form): the digit-product mix of the v3 projection kernel, S slices, tile 128 x NT,
 // one A digit times up to 256 / NT B digit planes per instruction; accumulators at columns 0.., A digits at column 480..
-template <int S, int NT>
+template <int S, int NT, int COMMITS>
 __global__ void __launch_bounds__(160, 1) i8_rate_ts_mix(int iters, long long* clocks) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, dummy[8];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int e = tid; e < (6 * 4096 + 512 * 32) / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(smem)[e] = 0x01020304u * (e % 61 + 1);
     fence_proxy_async_smem();
     if (warp == 4) {
         tmem_alloc(&tmem_base_s, 512);
-        if (tid == 128) { mbar_init(&bar, 1); fence_barrier_init(); }
+        if (tid == 128) { mbar_init(&bar, 1); for (int q = 0; q < 8; ++q) mbar_init(&dummy[q], 1); fence_barrier_init(); }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    constexpr int G = 256 / NT;
+    constexpr int G = (256 / NT) < S ? (256 / NT) : S;
     if (tid == 128) {
         const uint32_t sb = smem_u32(smem) + 6 * 4096;
         long long t0 = clock64();
@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(160, 1) i8_rate_ts_mix(int iters, long long* c
                     mma_i8_ts(tmem_base + (qa + qb0) * NT, tmem_base + 512 - 8 * S + qa * 8, smem_desc(sb + qb0 * NT * 32, kLBO, kSBO),
                               idesc_i8(1, 1, g * NT), 1u);
                 }
+#pragma unroll
+            for (int q = 0; q < COMMITS; ++q) mma_commit(&dummy[(i + q) & 7]);     // nobody waits on these: cost of the commit itself
         }
         mma_commit(&bar);
         mbar_wait(&bar, 0);
@@ -145,15 +147,15 @@ __global__ void __launch_bounds__(160, 1) i8_rate_ts_mix(int iters, long long* c
     if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
-template <int S, int NT>
+template <int S, int NT, int COMMITS>
 static void run_ts_mix(int sms, long long* dclk) {
     const int smem = 6 * 4096 + 512 * 32, iters = 20000;
-    cudaFuncSetAttribute(i8_rate_ts_mix<S, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(i8_rate_ts_mix<S, NT, COMMITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    i8_rate_ts_mix<S, NT><<<sms, 160, smem>>>(100, dclk);
+    i8_rate_ts_mix<S, NT, COMMITS><<<sms, 160, smem>>>(100, dclk);
     cudaEventRecord(e0);
-    i8_rate_ts_mix<S, NT><<<sms, 160, smem>>>(iters, dclk);
+    i8_rate_ts_mix<S, NT, COMMITS><<<sms, 160, smem>>>(iters, dclk);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(err)); exit(1); }
@@ -163,8 +165,8 @@ static void run_ts_mix(int sms, long long* dclk) {
     cudaMemcpy(clk.data(), dclk, sms * sizeof(long long), cudaMemcpyDeviceToHost);
     double cavg = 0; for (auto c : clk) cavg += (double)c; cavg /= sms;
     const double macs = 128.0 * NT * 32 * (S * (S + 1) / 2);
-    printf("  {\"ts_mix\": true, \"S\": %d, \"NT\": %d, \"clk_per_kstep\": %.1f, \"clk_per_column\": %.2f, \"int8_tops\": %.1f, \"macs_per_clk_per_sm\": %.0f},\n",
-           S, NT, cavg / iters, cavg / iters / NT, 2.0 * macs * iters * sms / (ms * 1e-3) / 1e12, macs / (cavg / iters));
+    printf("  {\"ts_mix\": true, \"commits_per_step\": %d, \"S\": %d, \"NT\": %d, \"clk_per_kstep\": %.1f, \"clk_per_column\": %.2f, \"int8_tops\": %.1f, \"macs_per_clk_per_sm\": %.0f},\n",
+           COMMITS, S, NT, cavg / iters, cavg / iters / NT, 2.0 * macs * iters * sms / (ms * 1e-3) / 1e12, macs / (cavg / iters));
 }
 
 template <int N, int NROT>
@@ -201,10 +203,14 @@ int main() {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     printf("{\"sms\": %d, \"clock_khz\": %d, \"runs\": [\n", sms, khz);
-    run_ts_mix<5, 80>(sms, dclk);
-    run_ts_mix<6, 64>(sms, dclk);
-    run_ts_mix<4, 112>(sms, dclk);
-    run_ts_mix<4, 96>(sms, dclk);
+    run_ts_mix<5, 80, 0>(sms, dclk);
+    run_ts_mix<5, 80, 1>(sms, dclk);
+    run_ts_mix<5, 80, 2>(sms, dclk);
+    run_ts_mix<5, 48, 0>(sms, dclk);
+    run_ts_mix<5, 48, 1>(sms, dclk);
+    run_ts_mix<5, 48, 2>(sms, dclk);
+    run_ts_mix<6, 64, 0>(sms, dclk);
+    run_ts_mix<4, 112, 0>(sms, dclk);
     run_unrolled<256, 1>(sms, dclk, false);
     run_unrolled<256, 2>(sms, dclk, false);
     run_unrolled<240, 2>(sms, dclk, false);
