@@ -12,7 +12,7 @@ __host__ __device__ constexpr long plane_stride(long ext) { return (ext + TABLE_
 
 // Tile shapes per slice count S.  Every kernel keeps S int32 accumulators (one per significance level) of NT TMEM columns.
 //   * projection (ozaki.cu, A operand generated into tensor memory): NTP sensor rows per tile; the A digits need
-//     NABUF x S x 8 TMEM columns (NABUF-deep: the commit -> producer -> tcgen05.st -> MMA hand-off latency is ~3 K steps),
+//     NABUF x S x 8 TMEM columns (double buffered; deeper buffers with narrower tiles measured slower),
 //     S * NTP + NABUF * 8 * S <= 512.  NTP is also the row-tile size of the sensitivities' digit blocks in memory.
 //   * GEMM with both operands in shared memory (ozaki_gemm.cu): NT output columns, S * NT <= 512, STAGES-deep ring.
 template <int S> struct Cfg;
