@@ -60,7 +60,7 @@ def read_peaks():
 
 class ClockSampler:
     """SM clocks / throttle reasons / power sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is
-    polled in-process every 10 ms (no process spawn inside or next to the timed region: starting `nvidia-smi` takes
+    polled in-process every 50 ms (no process spawn inside or next to the timed region: starting `nvidia-smi` takes
     NVML/driver locks for hundreds of ms on a multi-GPU box and stalls the CUDA calls of every rank); `nvidia-smi
     -lms` is the fallback when the NVML bindings are missing."""
 
@@ -128,7 +128,7 @@ class ClockSampler:
                 self.rows.append([str(self.device), sm, self.max_sm, pw, ""] + ["Active" if mask & bit else "Not Active" for _, bit in names])
             except Exception:
                 pass
-            self.stop_flag.wait(0.01)
+            self.stop_flag.wait(0.05)
 
     def _read(self):
         for line in self.proc.stdout:

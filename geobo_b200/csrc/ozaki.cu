@@ -11,19 +11,22 @@
 // into the fp64 result with an exact int64 recombination.  The only error is the truncation of the operands
 // to 7 + 8(S-1) bits (S = 5: 2^-39 relative to the row / table scale) and of levels >= S.
 //
-// CTA = 5 + W warps, persistent (one CTA per SM): warps 0-3 epilogue (TMEM -> int64 -> fp64 read-modify-write of
-// the Pt tile), warp 4 TMEM allocator + single-thread MMA issuer, warps 5.. producers; producer warp w owns the
-// pipeline stages st = w (mod W) (STAGES is a multiple of W, so one warp sees every use of its stages in order
-// and mbarrier parities stay unambiguous) and fills a whole K = 32 stage on its own, so W stages are in flight:
-//   * A digits: stored in global memory PRE-TILED in the UMMA canonical (K-major, no-swizzle) layout
-//     [row tile][k step][digit][4096 B], so one stage of A is one contiguous S * 4096-byte block fetched with a
-//     single bulk async copy (cp.async.bulk -> SASS UBLKCP) that signals the stage's mbarrier (complete_tx);
-//   * K digits are GENERATED: for 16 consecutive output voxels i and 16 consecutive contraction voxels j (both in
-//     one z-column, z fastest) the 16 x 16 digit block is Toeplitz in the stationary-covariance byte table --
-//     47 table bytes.  A half-warp loads the aligned words of that stretch once (one 32-bit load per lane), every
-//     lane picks its own unaligned 16-byte window with five shuffles + funnel shifts and stores it straight into
-//     the canonical layout (one conflict-free 16-byte st.shared per lane, digit and 16-column segment).
-// Stage hand-off is mbarrier based (full: producer warp + bulk-copy bytes -> MMA, empty: tcgen05.commit -> producer).
+// Tile = 128 voxel columns (M side) x NT sensor rows (N side); CTA = 18 warps, persistent (one CTA per SM):
+//   * warps 6-17, covariance-digit producers: the M-side operand is GENERATED and written straight into TENSOR MEMORY
+//     (tcgen05.st), from where the MMA reads its A operand -- no shared-memory traffic for it.  For 16 consecutive output
+//     voxels i and 16 consecutive contraction voxels j (both in one z-column, z fastest) the 16 x 16 digit block is
+//     Toeplitz in the stationary-covariance byte table (31 table bytes): a half-warp loads the aligned words once (one
+//     32-bit load per lane), every lane picks its unaligned 16-byte window with five shuffles + funnel shifts.  A warp
+//     owns one TMEM lane quarter and every third K step; lattice ids are prefetched two own steps ahead, table words one.
+//   * warp 5, one lane: the N-side operand (sensitivity digits, stored in global memory PRE-TILED in the UMMA canonical
+//     K-major no-swizzle layout [row tile of NT][k step][digit][NT x 32 B]) is one contiguous block per K step, fetched
+//     with a single bulk async copy (cp.async.bulk -> SASS UBLKCP) into a deep shared-memory ring;
+//   * warp 4, MMA issue: the whole warp runs the uniform loop with running ring state, one elected lane issues; one A
+//     digit (TMEM) times up to 256 / NT consecutive B digit planes per instruction; ONE full / done mbarrier pair and
+//     ONE tcgen05.commit per K step release the TMEM A buffer and the shared-memory stage together;
+//   * warps 0-3, epilogue: TMEM -> exact int64 recombination -> fp64 read-modify-write of the Pt tile (32 lanes write 32
+//     consecutive doubles of one Pt row).
+// TMEM: S x NT accumulator columns + 2 x S x 8 columns of double-buffered A digits (480 of 512 at S = 5, NT = 80).
 #include <stdlib.h>
 
 #include "common.cuh"
