@@ -48,7 +48,8 @@ METRIC = "voxels/sec joint-inversion (cov+chol+solve)"
 
 def read_peaks():
     peaks = {}
-    for name in ("MEASURED_PEAKS.json", os.path.join("profiles", "fp64_peaks_r1.json"), os.path.join("profiles", "int8_peaks_r1.json")):
+    for name in ("MEASURED_PEAKS.json", os.path.join("profiles", "fp64_peaks_r1.json"), os.path.join("profiles", "int8_peaks_r1.json"),
+                 os.path.join("profiles", "traffic_r1.json")):
         p = os.path.join(ROOT, name)
         if os.path.exists(p):
             try:

@@ -562,11 +562,6 @@ __global__ void dot_self_kernel(const double* __restrict__ ysol, long M, double*
     if (threadIdx.x == 0) *out = red[0];
 }
 
-__global__ void set_identity_kernel(double* __restrict__ X, long n) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) X[i * n + i] = 1.0;
-}
-
 static gemm::Task mk(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int M, int N, int K, int lower) {
     gemm::Task t;
     memset(&t, 0, sizeof t);
@@ -717,9 +712,10 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     }
     if (int8_var) {
         // ---- variance and mean without ever forming V = L^-1 Pt (:114-117) in memory:
-        //   Linv = L^-1 explicitly (fp64 blocked solve against the identity), alpha = Linv^T u,
-        //   one pass over Pt: transposed digit blocks + mu = Pt^T alpha (:115),
-        //   colsumsq(Linv . Pt) on the int8 tensor cores with the reduction in the epilogue (:117, diag only).
+        //   Linv = L^-1 explicitly (recursive doubling from the diagonal-block inverses), u = Linv y, alpha = Linv^T u,
+        //   refinement of alpha against the fp64 matrix-free operator and mu = K A3^T alpha (:115),
+        //   one pass over Pt for its transposed digit blocks, then colsumsq(Linv . Pt) on the int8 tensor cores with the
+        //   reduction in the epilogue (:117, diag only).
         const int S = h->slices;
         if (p->var_slices != S) {
             if (p->l8) { gb_dev_free(ctx, p->l8); p->l8 = nullptr; }

@@ -90,17 +90,22 @@ extern "C" int gb_comm_allgather(gb_ctx* ctx, const double* local, int64_t count
     if (!ctx->nccl_comm || !g_nccl.all_gather) return gb_fail(ctx, GB_ERR_NCCL, "gb_comm_allgather without gb_comm_init");
     GB_CUDA(ctx, cudaSetDevice(ctx->device));
     void *send = nullptr, *recv = nullptr;
-    GB_CUDA(ctx, gb_dev_malloc(ctx, &send, (size_t)count * sizeof(double)));
-    GB_CUDA(ctx, gb_dev_malloc(ctx, &recv, (size_t)count * ctx->nranks * sizeof(double)));
-    GB_CUDA(ctx, cudaMemcpyAsync(send, local, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    const int ncclFloat64 = 8;
-    int rc = g_nccl.all_gather(send, recv, (size_t)count, ncclFloat64, ctx->nccl_comm, ctx->stream);
-    if (rc != 0) return gb_fail(ctx, GB_ERR_NCCL, "ncclAllGather: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
-    GB_CUDA(ctx, cudaMemcpyAsync(out, recv, (size_t)count * ctx->nranks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    gb_dev_free(ctx, send);
+    int rc_out = GB_OK;
+    cudaError_t e = gb_dev_malloc(ctx, &send, (size_t)count * sizeof(double));
+    if (e == cudaSuccess) e = gb_dev_malloc(ctx, &recv, (size_t)count * ctx->nranks * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(send, local, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const int ncclFloat64 = 8;
+        const int rc = g_nccl.all_gather(send, recv, (size_t)count, ncclFloat64, ctx->nccl_comm, ctx->stream);
+        if (rc != 0) rc_out = gb_fail(ctx, GB_ERR_NCCL, "ncclAllGather: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    }
+    if (e == cudaSuccess && rc_out == GB_OK)
+        e = cudaMemcpyAsync(out, recv, (size_t)count * ctx->nranks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    gb_dev_free(ctx, send);       // both back to the context's cache, also on the error paths
     gb_dev_free(ctx, recv);
-    return GB_OK;
+    if (e != cudaSuccess) return gb_fail(ctx, e == cudaErrorMemoryAllocation ? GB_ERR_NOMEM : GB_ERR_CUDA, "gb_comm_allgather: %s", cudaGetErrorString(e));
+    return rc_out;
 }
 
 void comm_destroy(gb_ctx* ctx) {

@@ -31,23 +31,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// non-blocking probe (mbarrier.test_wait): no hardware suspend, for latency-critical hand-offs
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; spin < (1u << 30); ++spin)
-        if (mbar_test_wait(bar, parity)) return;
-    __trap();
-}
 // Bounded wait: a protocol bug must never hang the GPU -- trap instead (kills only this context).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0; spin < (1u << 28); ++spin)
