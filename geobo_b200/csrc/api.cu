@@ -672,7 +672,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
             GB_CUDA(ctx, ozaki_gemm_store(p->b8 + t * blk, p->b_exp + t * Ns, ks, 0, p->a8[c], p->a_exp[c], a_ksteps, a_k0, ks, (int)Ns, (int)Ns,
                                           p->Bm + (long)cp_ * Ns * Mp + (long)c * Ns, Mp, c == cp_ ? 1 : 0, S, ctx->sm_count, s));
         }
-        p->nlaunch += 8;
+        p->nlaunch += 9;                  // 3 x (row absmax, row slicing, GEMM)
         if (p->nd) {
             dim3 grid((unsigned)((M + 255) / 256), (unsigned)p->nd);
             drill_rows_aka_kernel<<<grid, 256, 0, s>>>(p->Pt, ldp, ncp, p->drill_dev, p->c0, p->c1, 2 * Ns, M, p->Bm, Mp);
@@ -758,7 +758,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         for (int itr = 0; itr <= nref; ++itr) {
             GB_CUDA(ctx, refine_at_alpha(ra, p->alpha, p->rf_w, s));       // w = A3^T alpha
             GB_CUDA(ctx, refine_kw(ra, p->rf_w, p->rf_z, s));              // z = K w   (this rank's voxel columns)
-            p->nlaunch += 3 + (p->nd ? 1 : 0);
+            p->nlaunch += 3 + (refine_kw_slices(ncol) > 1 ? 1 : 0) + (p->nd ? 1 : 0);
             if (itr == nref) break;                                        // z = K A3^T alpha = posterior mean
             GB_CUDA(ctx, refine_a_z(ra, p->rf_z, rt, s));                  // t = A3 z  (partial over this rank's columns)
             GB_TRY(comm_allreduce_sum_f64(ctx, rt, (size_t)Mp));
@@ -773,7 +773,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         GB_CUDA(ctx, ozaki_colsumsq_tri(p->l8, p->l_exp, p->b8, p->b_exp, (int)Mp, ldp, S, p->partial, p->vscratch, ctx->sm_count, s));
         GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
         GB_CUDA(ctx, ozaki_var_finalize(p->partial, (int)(Mp / 128), ldp, ncp, ncol, h->gp_amp, p->var, s));
-        p->nlaunch += 10;
+        p->nlaunch += 11;                 // u / alpha (2), two dots, mean scatter, 2 x 2 slicing kernels, colsumsq GEMM, variance
     } else if (full) {
         // ---- V = L^-1 Pt (:114) in place, then mean (:115) and variance diagonal (:117)
         GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->Pt, ldp, (int)ldp, p->tmp, s));
