@@ -336,6 +336,9 @@ struct gb_problem {
     int* b_exp = nullptr;
     double* partial = nullptr;           // [Mp/128][ldp]
     double* vscratch = nullptr;          // running sums of V when Mp > 16384 (several accumulator flushes)
+    double* chol_stage = nullptr;        // packed panel of the distributed Cholesky
+    double* chol_pan = nullptr;
+    int* chol_paninfo = nullptr;
     int var_slices = 0;
     size_t b8_bytes = 0;
     // fp64 matrix-free refinement scratch
@@ -370,7 +373,7 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
     void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
                     p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp,
                     p->Linv, p->tmpL, p->alpha, p->l8, p->l_exp, p->b8, p->b_exp, p->partial,
-                    p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch,
+                    p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch, p->chol_stage, p->chol_pan, p->chol_paninfo,
                     p->linv, p->scal, p->info, p->mu, p->var};
     for (void* q : ptrs)
         if (q) gb_dev_free(p->ctx, q);
@@ -701,7 +704,21 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     // ---- Cholesky (inversion.py:100) and u = L^-1 y (:105)
     CholWork w;
     w.linv = p->linv; w.logdet = p->scal; w.info = p->info;
-    GB_CUDA(ctx, chol_factor(p->Bm, Mp, (int)Mp, (int)M, w, s));
+    // multi-GPU: block-cyclic factorisation with NCCL panel broadcasts once the matrix is large enough for the trailing
+    // updates to matter (M >= 8192), replicated otherwise (the per-panel broadcast latency would dominate);
+    // GEOBO_B200_DIST_CHOL=1/0 forces either.
+    bool dist_chol = ctx->nranks > 1 && Mp >= 8192;
+    if (const char* e = getenv("GEOBO_B200_DIST_CHOL")) dist_chol = ctx->nranks > 1 && atoi(e) != 0;
+    if (dist_chol) {
+        if (!p->chol_stage) {
+            GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->chol_stage, ((size_t)Mp * 128 + 128 * 128) * sizeof(double)));
+            GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->chol_pan, (size_t)2 * (Mp / 128) * sizeof(double)));
+            GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->chol_paninfo, (size_t)(Mp / 128) * sizeof(int)));
+        }
+        GB_TRY(chol_factor_dist(ctx, p->Bm, Mp, (int)Mp, (int)M, w, p->chol_stage, p->chol_pan, p->chol_paninfo, s));
+    } else {
+        GB_CUDA(ctx, chol_factor(p->Bm, Mp, (int)Mp, (int)M, w, s));
+    }
     GB_CUDA(ctx, cudaEventRecord(p->ev[6], s));
     const bool int8_var = full && h->slices != 0;
     if (!int8_var) {

@@ -7,6 +7,7 @@
 // only) on the DMMA engine.  The triangular solve with 3N right-hand sides is left-looking: each
 // 128-row block of V is one wide GEMM against all previous rows, then a GEMM with the block inverse.
 #include "common.cuh"
+#include "comm.h"
 
 #include <algorithm>
 #include <utility>
@@ -259,6 +260,107 @@ cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork&
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------- distributed factorisation
+// 1-D block-cyclic Cholesky over the ranks of the context: column block kb (128 columns) is owned by
+// rank kb % nranks.  Per panel: the owner factors the diagonal block (potrf128) and solves the panel, packs
+// [L[k0:, kb] | inverse of the diagonal block] into a contiguous staging buffer, ONE ncclBroadcast over NVLink ships it,
+// every rank unpacks it into its replica of L and updates only the trailing column blocks it owns (one batched GEMM
+// launch on the fp64 tensor pipe, operand = the packed panel).  L and the block inverses end up replicated, which is what
+// the triangular inverse / refinement stages need.  log det and the first non-positive pivot are combined by all-reduce.
+__global__ void panel_pack_kernel(const double* __restrict__ Bm, long ldb, int k0, int rows, const double* __restrict__ linv,
+                                  double* __restrict__ stage) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long np = (long)rows * NB;
+    if (e < np) stage[e] = Bm[(long)(k0 + e / NB) * ldb + k0 + (e % NB)];
+    else if (e < np + NB * NB) stage[e] = linv[e - np];
+}
+
+__global__ void panel_unpack_kernel(double* __restrict__ Bm, long ldb, int k0, int rows, double* __restrict__ linv,
+                                    const double* __restrict__ stage) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long np = (long)rows * NB;
+    if (e < np) Bm[(long)(k0 + e / NB) * ldb + k0 + (e % NB)] = stage[e];
+    else if (e < np + NB * NB) linv[e - np] = stage[e];
+}
+
+// per-panel log det / pivot info -> doubles for the sum all-reduce (only the owner of a panel has non-zero entries)
+__global__ void chol_pan_to_double_kernel(const int* __restrict__ paninfo, int nblk, double* __restrict__ pan) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nblk) pan[nblk + k] = (double)paninfo[k];
+}
+
+// total log det in panel order (same summation order as the single-GPU factorisation) and the first non-positive pivot
+__global__ void chol_pan_finalize_kernel(const double* __restrict__ pan, int nblk, double* __restrict__ logdet, int* __restrict__ info) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s = 0.0;
+    int first = 0;
+    for (int k = 0; k < nblk; ++k) {
+        s += pan[k];
+        const int v = (int)pan[nblk + k];
+        if (v > 0 && first == 0) first = v;
+    }
+    *logdet += s;
+    if (first && *info == 0) *info = first;
+}
+
+// stage: [Mp * 128 + 128 * 128] doubles, pan: [2 * Mp / 128] doubles, paninfo: [Mp / 128] ints (all device scratch)
+int chol_factor_dist(gb_ctx* ctx, double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, double* stage, double* pan, int* paninfo,
+                     cudaStream_t s) {
+    static bool attr_set = false;
+    const int smem = (NB * PLD + 64 * 64 + NB) * (int)sizeof(double);
+    if (!attr_set) {
+        GB_CUDA(ctx, cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int nblk = Mp / NB, nr = ctx->nranks, me = ctx->rank;
+    GB_CUDA(ctx, cudaMemsetAsync(pan, 0, (size_t)2 * nblk * sizeof(double), s));
+    GB_CUDA(ctx, cudaMemsetAsync(paninfo, 0, (size_t)nblk * sizeof(int), s));
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k0 = kb * NB, rows = Mp - k0, owner = kb % nr;
+        double* linv = w.linv + (long)kb * NB * NB;
+        const long count = (long)rows * NB + NB * NB;
+        if (me == owner) {
+            potrf128_kernel<<<1, 256, smem, s>>>(Bm, ldb, k0, Mtrue, linv, pan + kb, paninfo + kb);
+            GB_CUDA(ctx, cudaGetLastError());
+            if (rows > NB) {
+                double* panel = Bm + (long)(k0 + NB) * ldb + k0;
+                gemm::TaskBatch b1;
+                b1.n = 1;
+                b1.t[0] = make_task(panel, ldb, linv, NB, nullptr, 0, panel, ldb, rows - NB, NB, NB, 1.0, 0.0, 0);
+                GB_CUDA(ctx, gemm::launch(b1, gemm::B_T, s));
+            }
+            panel_pack_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(Bm, ldb, k0, rows, linv, stage);
+            GB_CUDA(ctx, cudaGetLastError());
+        }
+        GB_TRY(comm_broadcast_f64(ctx, stage, (size_t)count, owner));
+        if (me != owner) {
+            panel_unpack_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(Bm, ldb, k0, rows, linv, stage);
+            GB_CUDA(ctx, cudaGetLastError());
+        }
+        // trailing update of the column blocks this rank owns: A[j0:, jb] -= L[j0:, kb] . L[jb rows, kb]^T, operands from the packed panel
+        gemm::TaskBatch b2;
+        b2.n = 0;
+        for (int jb = kb + 1; jb < nblk; ++jb) {
+            if (jb % nr != me) continue;
+            const int j0 = jb * NB;
+            const double* pj = stage + (long)(j0 - k0) * NB;          // rows j0.. of the packed panel (ld = NB)
+            double* c = Bm + (long)j0 * ldb + j0;
+            b2.t[b2.n++] = make_task(pj, NB, pj, NB, c, ldb, c, ldb, Mp - j0, NB, NB, -1.0, 1.0, 0);
+            if (b2.n == gemm::MAX_TASKS) {
+                GB_CUDA(ctx, gemm::launch(b2, gemm::B_T, s));
+                b2.n = 0;
+            }
+        }
+        if (b2.n) GB_CUDA(ctx, gemm::launch(b2, gemm::B_T, s));
+    }
+    chol_pan_to_double_kernel<<<(nblk + 127) / 128, 128, 0, s>>>(paninfo, nblk, pan);
+    GB_CUDA(ctx, cudaGetLastError());
+    GB_TRY(comm_allreduce_sum_f64(ctx, pan, (size_t)2 * nblk));
+    chol_pan_finalize_kernel<<<1, 32, 0, s>>>(pan, nblk, w.logdet, w.info);
+    GB_CUDA(ctx, cudaGetLastError());
+    return GB_OK;
 }
 
 cudaError_t chol_forward_solve(const double* L, long ldl, int Mp, const CholWork& w, double* Pt, long ldp, int ncols_all,

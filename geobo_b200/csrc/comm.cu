@@ -12,6 +12,7 @@ typedef int (*fn_getuid)(ncclUniqueId_*);
 typedef int (*fn_initrank)(void**, int, ncclUniqueId_, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*fn_broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_destroy)(void*);
 typedef const char* (*fn_errstr)(int);
 
@@ -21,6 +22,7 @@ struct NcclApi {
     fn_initrank init_rank = nullptr;
     fn_allreduce all_reduce = nullptr;
     fn_allgather all_gather = nullptr;
+    fn_broadcast broadcast = nullptr;
     fn_destroy destroy = nullptr;
     fn_errstr errstr = nullptr;
 } g_nccl;
@@ -37,6 +39,7 @@ int load_nccl(gb_ctx* ctx) {
     g_nccl.init_rank = (fn_initrank)dlsym(g_nccl.handle, "ncclCommInitRank");
     g_nccl.all_reduce = (fn_allreduce)dlsym(g_nccl.handle, "ncclAllReduce");
     g_nccl.all_gather = (fn_allgather)dlsym(g_nccl.handle, "ncclAllGather");
+    g_nccl.broadcast = (fn_broadcast)dlsym(g_nccl.handle, "ncclBroadcast");
     g_nccl.destroy = (fn_destroy)dlsym(g_nccl.handle, "ncclCommDestroy");
     g_nccl.errstr = (fn_errstr)dlsym(g_nccl.handle, "ncclGetErrorString");
     if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.all_reduce || !g_nccl.destroy)
@@ -76,6 +79,16 @@ int comm_allreduce_sum_f64(gb_ctx* ctx, double* buf, size_t count) {
     const int ncclFloat64 = 8, ncclSum = 0;
     int rc = g_nccl.all_reduce(buf, buf, count, ncclFloat64, ncclSum, ctx->nccl_comm, ctx->stream);
     if (rc != 0) return gb_fail(ctx, GB_ERR_NCCL, "ncclAllReduce: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    return GB_OK;
+}
+
+// In-place broadcast of `count` doubles from `root` on the context stream (Cholesky panels of the distributed factorisation)
+int comm_broadcast_f64(gb_ctx* ctx, double* buf, size_t count, int root) {
+    if (ctx->nranks <= 1) return GB_OK;
+    if (!ctx->nccl_comm || !g_nccl.broadcast) return gb_fail(ctx, GB_ERR_NCCL, "multi-rank problem without gb_comm_init");
+    const int ncclFloat64 = 8;
+    int rc = g_nccl.broadcast(buf, buf, count, ncclFloat64, root, ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return gb_fail(ctx, GB_ERR_NCCL, "ncclBroadcast: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
     return GB_OK;
 }
 

@@ -193,6 +193,9 @@ struct CholWork {
     int* info = nullptr;      // device scalar: first non-positive pivot (1-based), 0 = ok
 };
 cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, cudaStream_t s);
+// 1-D block-cyclic factorisation over the ranks of the context (one ncclBroadcast per 128-column panel); L ends up replicated
+int chol_factor_dist(gb_ctx* ctx, double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, double* stage, double* pan, int* paninfo,
+                     cudaStream_t s);
 // V = L^-1 Pt in place (Pt: [Mp][ldp]); tmp: [128][ldp]
 // Linv = L^-1 (lower triangular, Mp x Mp, ld = Mp) by recursive doubling from the 128 x 128 diagonal-block inverses that
 // chol_factor left in w.linv: [L11 0; L21 L22]^-1 = [X11 0; -X22 L21 X11, X22]; two batched GEMM launches per level.
