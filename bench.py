@@ -240,8 +240,8 @@ def run_ours(args):
     gl0 = inv2.gp_length.copy()
     inv2.cubing(f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"])   # warm-up
     dist.barrier()
-    sampler2 = ClockSampler(ctx_device())
-    sampler2.start()
+    # no NVML polling inside this region: it is host-latency sensitive (problem build = many synchronous driver calls) and
+    # NVML queries share driver locks with them; the clocks of the device-timed region above are the ones reported
     t0 = time.perf_counter()
     e2e_dev_ms = 0.0
     for _ in range(e2e_steps):
@@ -249,13 +249,12 @@ def run_ours(args):
         cubes = inv2.cubing(f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"])
         e2e_dev_ms += inv2.timings["total"]
     e2e_s = dist.max_over_ranks(time.perf_counter() - t0)
-    e2e_clocks = sampler2.stop()
     dist.barrier()
     M = 2 * Ns + nd
     h2d = 8 * (f["grav"].size + f["mag"].size + f["sensor_locations"].size + inv2.Edges.size + M) + 8 * nd
     d2h = 8 * (6 * (c1 - c0) + 2) + 4
     e2e = {"value": N * e2e_steps / e2e_s, "unit": "voxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "steps": e2e_steps, "ms_per_step": e2e_s * 1e3 / e2e_steps, "device_ms_per_step": e2e_dev_ms / e2e_steps, "clocks": e2e_clocks,
+           "steps": e2e_steps, "ms_per_step": e2e_s * 1e3 / e2e_steps, "device_ms_per_step": e2e_dev_ms / e2e_steps,
            "includes": "device problem build (A_sens x2 on GPU), H2D of data/geometry, predict3 stage, D2H of 6 cubes"}
     finite = bool(all(np.isfinite(cb).all() for cb in cubes[:2]))
 
