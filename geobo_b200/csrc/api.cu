@@ -456,7 +456,13 @@ extern "C" int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* d, gb_probl
     // sensitivities (inversion.py:223-224) computed on the device; edges/locations are the only H2D traffic
     {
         const int64_t nedge = (xN + 1) * (yN + 1) * (zN + 1);
-        DevBuf<double> e, l;
+        // scratch from the context's cache (a plain cudaMalloc / cudaFree pair per problem costs a device synchronisation)
+        struct Scratch {
+            gb_ctx* c; double* p = nullptr;
+            explicit Scratch(gb_ctx* c_) : c(c_) {}
+            cudaError_t alloc(size_t n) { return gb_dev_malloc(c, (void**)&p, n * sizeof(double)); }
+            ~Scratch() { gb_dev_free(c, p); }
+        } e(ctx), l(ctx);
         PCUDA(e.alloc(3 * nedge));
         PCUDA(l.alloc(3 * p->Ns));
         PCUDA(cudaMemcpyAsync(e.p, d->edges, 3 * nedge * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
