@@ -79,3 +79,69 @@ def sliced_matmul(A, B, S, chunk=16384):
         scale = np.ldexp(1.0, (ea[:, None] + eb[None, :] - 14 - 8 * (S - 1)).astype(np.int64))
         C += scale * np.asarray(acc, dtype=np.float64)
     return C, worst
+
+
+def predict_sliced(A_list, didx, kcov, y, sig, amp, S, refine=1):
+    """CPU restatement of the device pipeline of `precision: int8xS` on a small dense problem:
+    Pt = A3.K, AkA and L^-1.Pt as digit-slice products (exact integer accumulation of S balanced digits per operand,
+    `sliced_matmul`), fp64 Cholesky, `refine` steps of iterative refinement of alpha = (A K A^T + Sigma)^-1 y against
+    the fp64 operator, mean = K A3^T alpha, variance = amp - colsumsq(Linv . Pt).
+
+    A_list = [A_grav, A_magn] (Ns x N), didx = drilled voxel indices, kcov = dense 3N x 3N covariance (fp64, from the
+    oracle), y = data vector.  Returns (mu, var).  Used by tests/test_digit_slices.py to check the ERROR MODEL of the
+    scheme against the oracle's fp64 predict3 (inversion.py:96-117) without a GPU."""
+    from scipy.linalg import cholesky, solve_triangular
+    Ns, N = A_list[0].shape
+    nd = len(didx)
+    M = 2 * Ns + nd
+    K = np.asarray(kcov).reshape(3, N, 3, N)
+    # Pt[(c, s), (r, i)] = sum_j A_c[s, j] K[(c, j), (r, i)]  -- one exponent per sensor row and per covariance block
+    Pt = np.zeros((M, 3 * N))
+    for c in range(2):
+        for r in range(3):
+            Kb = K[c, :, r, :]                       # (j, i)
+            scale = 2.0 ** scale_exp(np.abs(Kb).max())
+            P, worst = sliced_matmul(A_list[c], (Kb / scale).T, S)       # operands: rows = A rows, rows = output voxels i
+            assert worst < 2 ** 31
+            Pt[c * Ns:(c + 1) * Ns, r * N:(r + 1) * N] = P * scale
+    for r in range(3):
+        Pt[2 * Ns:, r * N:(r + 1) * N] = K[2, didx, r, :]                 # one-hot drill rows: exact gathers
+    # AkA: block (c', c) = Pt[(c', .), (c, .)] . A_c^T  as digit-slice products; drill rows / columns are gathers
+    AkA = np.zeros((M, M))
+    for cp in range(2):
+        for c in range(2):
+            blk, _ = sliced_matmul(Pt[cp * Ns:(cp + 1) * Ns, c * N:(c + 1) * N], A_list[c], S)
+            AkA[cp * Ns:(cp + 1) * Ns, c * Ns:(c + 1) * Ns] = blk
+    AkA[2 * Ns:, :] = Pt[:, 2 * N + np.asarray(didx, dtype=int)].T if nd else AkA[2 * Ns:, :]
+    AkA[:, 2 * Ns:] = AkA[2 * Ns:, :].T
+    AkA = np.tril(AkA) + np.tril(AkA, -1).T                               # the device only forms the lower triangle
+    sig2 = np.hstack((np.full(Ns, sig[0] ** 2), np.full(Ns, sig[1] ** 2), np.full(nd, sig[2] ** 2)))
+    AkA[np.diag_indices(M)] += sig2
+    L = cholesky(AkA, lower=True)
+    Linv = solve_triangular(L, np.eye(M), lower=True)
+    alpha = Linv.T @ (Linv @ y)
+
+    def a3t(v):                                                            # A3^T v
+        w = np.zeros(3 * N)
+        w[:N] = A_list[0].T @ v[:Ns]
+        w[N:2 * N] = A_list[1].T @ v[Ns:2 * Ns]
+        if nd:
+            w[2 * N + np.asarray(didx, dtype=int)] = v[2 * Ns:]
+        return w
+
+    def a3(z):                                                             # A3 z
+        t = np.empty(M)
+        t[:Ns] = A_list[0] @ z[:N]
+        t[Ns:2 * Ns] = A_list[1] @ z[N:2 * N]
+        if nd:
+            t[2 * Ns:] = z[2 * N + np.asarray(didx, dtype=int)]
+        return t
+
+    Kd = np.asarray(kcov)
+    for _ in range(refine):
+        r = y - a3(Kd @ a3t(alpha)) - sig2 * alpha                         # fp64 matrix-free residual
+        alpha = alpha + Linv.T @ (Linv @ r)
+    mu = Kd @ a3t(alpha)
+    V, _ = sliced_matmul(Linv, Pt.T.copy(), S)                            # rows of Linv x columns of Pt
+    var = amp - np.einsum("ij,ij->j", V, V)
+    return mu, var

@@ -48,3 +48,35 @@ def test_flush_interval_cannot_overflow_int32():
     A = np.full((1, 16384), -0.5)
     d = ds.balanced_digits(np.ldexp(A, -ds.scale_exp(0.5)), 6)
     assert d.min() >= -128
+
+
+@pytest.mark.parametrize("kf,S,tol_mu,tol_var", [("exp", 5, 1e-8, 1e-6), ("matern32", 5, 1e-8, 1e-6), ("exp", 4, 1e-5, 1e-4)])
+def test_sliced_pipeline_error_model_vs_fp64_oracle(kf, S, tol_mu, tol_var):
+    """The whole `precision: int8xS` pipeline restated on the CPU (digit-slice products + fp64 Cholesky + one refinement
+    step + matrix-free mean) against the oracle's fp64 predict3 on a small cube: the mean is independent of the operand
+    rounding after refinement, the variance error is the slice error."""
+    import json
+    from conftest import load_golden
+    from oracle import numpy_oracle as o
+    cfg = json.loads(str(load_golden("sens_8x6x5.npz")["cfg"]))
+    cfg.update(xNcube=4, yNcube=4, zNcube=8, kernelfunc=kf)
+    c = o.make_config(cfg)
+    E, vp = o.cube_geometry(c)
+    loc = o.sensor_grid(c)
+    Ag = o.a_sens(c, c.magneticField * 0, loc, E, "grav")
+    Am = o.a_sens(c, c.magneticField, loc, E, "magn")
+    N, Ns = Ag.shape[1], Ag.shape[0]
+    rng = np.random.default_rng(3)
+    didx = np.sort(rng.choice(N, 5, replace=False))
+    y = rng.standard_normal(2 * Ns + 5)
+    gl = c.gp_lengthscale * c.xvoxsize * (np.array([1.0, 1.01, 1.02]) if kf == "matern32" else np.ones(3))
+    sig, w, amp = np.asarray(c.gp_err, float), np.asarray(c.gp_coeff, float), 1.0
+    mu_ref, var_ref, _, _ = o.predict_lean(c, [Ag, Am], didx, y, gl.copy(), sig, w, amp)
+    pts = o.grid_points((c.xNcube, c.yNcube, c.zNcube), (c.xvoxsize, c.yvoxsize, c.zvoxsize))
+    kcov = amp * o.create_cov(o.sqdist(pts), gl.copy(), w, fkernel=kf)
+    mu, var = ds.predict_sliced([Ag, Am], didx, kcov, y, sig, amp, S, refine=1)
+    assert np.abs(mu - mu_ref).max() <= tol_mu * np.abs(mu_ref).max()
+    assert np.abs(var - var_ref).max() <= tol_var * np.abs(var_ref).max()
+    if S == 5:      # without refinement the mean carries the slice error of AkA and Pt
+        mu0, _ = ds.predict_sliced([Ag, Am], didx, kcov, y, sig, amp, S, refine=0)
+        assert np.abs(mu0 - mu_ref).max() >= np.abs(mu - mu_ref).max()
