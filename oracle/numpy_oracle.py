@@ -523,43 +523,37 @@ def spherical2cartes(x0, y0, z0, phi, theta, r):
 
 
 def futility_vertical(params, drill_rec, drill_var, kappa, beta, costs=None):
-    """geobo/run_geobo.py:175-200 (module globals made explicit)."""
-    if costs is None:
-        costs = drill_rec * 0.
-    params = np.asarray(params)
-    xmaxvox = drill_rec.shape[0] - 1
-    ymaxvox = drill_rec.shape[1] - 1
-    if np.isfinite(params).all():
-        xd = int(np.round(params[0]))
-        yd = int(np.round(params[1]))
-        if (xd > 0) & (xd < xmaxvox) & (yd > 0) & (yd < ymaxvox):
-            func = np.sum(drill_rec[xd, yd, :]) + kappa * np.sqrt(np.sum(drill_var[xd, yd, :])) - beta * np.sum(costs[xd, yd, :])
-        else:
-            func = -np.inf
-    else:
-        func = -np.inf
-    return -func
+    """Restates geobo/run_geobo.py:175-200 with the module globals made explicit: minus the upper-confidence utility
+    of a vertical hole through voxel column round(params), +inf for non-finite input or a border column."""
+    p = np.asarray(params, dtype=float)
+    if not np.all(np.isfinite(p)):
+        return np.inf
+    col = (int(np.round(p[0])), int(np.round(p[1])))
+    n0, n1 = drill_rec.shape[:2]
+    if not (0 < col[0] < n0 - 1 and 0 < col[1] < n1 - 1):
+        return np.inf
+    cost_term = 0.0 if costs is None else beta * np.sum(costs[col])
+    utility = np.sum(drill_rec[col]) + kappa * np.sqrt(np.sum(drill_var[col])) - cost_term
+    return -utility
 
 
 def futility_drill(params, drill_rec, drill_var, kappa, beta, c, costs=None):
-    """geobo/run_geobo.py:203-235 (``c``: config with voxel sizes, zLcube, zmax)."""
-    if costs is None:
-        costs = drill_rec * 0.
-    length_newdrill = c.zLcube
+    """Restates geobo/run_geobo.py:203-235 (``c``: config with voxel sizes, zLcube, zmax): a core of length zLcube from
+    (x0, y0, zmax) along (azimuth, dip) is sampled at int(2 L / min voxel size) points of np.linspace(0, L); the voxel
+    of a sample is the truncated quotient of its coordinates by the voxel sizes on axes (0, 1, 2) (negative indices wrap
+    as in NumPy indexing); any index outside the cube makes the reference's try/except return -0.0."""
+    length = c.zLcube
     x0, y0, azimuth, dip = params
-    nstep = int(2 * length_newdrill / np.min([c.xvoxsize, c.yvoxsize, c.zvoxsize]))
-    rladder = np.linspace(0, length_newdrill, nstep)
-    x0 = rladder * 0 + x0
-    y0 = rladder * 0 + y0
-    z0 = rladder * 0 + c.zmax
-    azimuth = rladder * 0 + azimuth
-    dip = rladder * 0 + dip
+    nstep = int(2 * length / min(c.xvoxsize, c.yvoxsize, c.zvoxsize))
+    r = np.linspace(0, length, nstep)
+    phi = (r * 0 + azimuth) * np.pi / 180.
+    theta = (180 - (r * 0 + dip)) * np.pi / 180.
+    px, py, pz = spherical2cartes(r * 0 + x0, r * 0 + y0, r * 0 + c.zmax, phi, theta, r)
+    with np.errstate(all="ignore"):
+        idx = ((px / c.xvoxsize).astype(int), (py / c.yvoxsize).astype(int), (-pz / c.zvoxsize).astype(int))
     try:
-        xd, yd, zd = spherical2cartes(x0, y0, z0, azimuth * np.pi / 180., (180 - dip) * np.pi / 180., rladder)
-        xnew = (xd / c.xvoxsize).astype(int)
-        ynew = (yd / c.yvoxsize).astype(int)
-        znew = (-zd / c.zvoxsize).astype(int)
-        funct = np.sum(drill_rec[xnew, ynew, znew]) + kappa * np.sqrt(np.sum(drill_var[xnew, ynew, znew])) - beta * np.sum(costs[xnew, ynew, znew])
+        total = np.sum(drill_rec[idx]) + kappa * np.sqrt(np.sum(drill_var[idx]))
+        total = total - beta * (np.sum(costs[idx]) if costs is not None else np.sum(drill_rec[idx] * 0.))
     except Exception:
-        funct = 0.
-    return -funct
+        total = 0.
+    return -total
