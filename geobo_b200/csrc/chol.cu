@@ -6,6 +6,8 @@
 // accumulates log det) -> panel solve as a GEMM with that inverse -> trailing update (lower tiles
 // only) on the DMMA engine.  The triangular solve with 3N right-hand sides is left-looking: each
 // 128-row block of V is one wide GEMM against all previous rows, then a GEMM with the block inverse.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "comm.h"
 
@@ -236,26 +238,46 @@ cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork&
         attr_set = true;
     }
     const int nblk = Mp / NB;
-    for (int kb = 0; kb < nblk; ++kb) {
-        const int k0 = kb * NB;
-        double* linv = w.linv + (long)kb * NB * NB;
-        potrf128_kernel<<<1, 256, smem, s>>>(Bm, ldb, k0, Mtrue, linv, w.logdet, w.info);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        const int rest = Mp - k0 - NB;
+    // GEOBO_B200_CHOL_OUTER = panels per outer block (1 = plain right-looking, the default; 4 = two-level blocking: the
+    // panels of a 512-wide block are factored left-looking and the trailing matrix is updated once per block with K = 512,
+    // which keeps the DMMA pipe busier than four K = 128 updates)
+    int outer = 1;
+    if (const char* ev = getenv("GEOBO_B200_CHOL_OUTER")) { outer = atoi(ev); if (outer < 1 || outer > 16) outer = 1; }
+    for (int ob = 0; ob < nblk; ob += outer) {
+        const int o0 = ob * NB, oe = (ob + outer < nblk ? ob + outer : nblk), o1 = oe * NB;
+        for (int kb = ob; kb < oe; ++kb) {
+            const int k0 = kb * NB;
+            double* linv = w.linv + (long)kb * NB * NB;
+            if (k0 > o0) {
+                // left-looking inside the outer block: A[k0:, kb] -= L[k0:, o0:k0] . L[kb rows, o0:k0]^T
+                double* c = Bm + (long)k0 * ldb + k0;
+                gemm::TaskBatch b0;
+                b0.n = 1;
+                b0.t[0] = make_task(Bm + (long)k0 * ldb + o0, ldb, Bm + (long)k0 * ldb + o0, ldb, c, ldb, c, ldb, Mp - k0, NB, k0 - o0, -1.0, 1.0, 0);
+                e = gemm::launch(b0, gemm::B_T, s);
+                if (e != cudaSuccess) return e;
+            }
+            potrf128_kernel<<<1, 256, smem, s>>>(Bm, ldb, k0, Mtrue, linv, w.logdet, w.info);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            const int rest = Mp - k0 - NB;
+            if (rest <= 0) break;
+            double* panel = Bm + (long)(k0 + NB) * ldb + k0;
+            // L21 = A21 . L11^-T : C[m, n] = sum_k A21[m, k] * Linv[n, k]   (in place: one CTA owns whole rows)
+            gemm::TaskBatch b1;
+            b1.n = 1;
+            b1.t[0] = make_task(panel, ldb, linv, NB, nullptr, 0, panel, ldb, rest, NB, NB, 1.0, 0.0, 0);
+            e = gemm::launch(b1, gemm::B_T, s);
+            if (e != cudaSuccess) return e;
+        }
+        const int rest = Mp - o1;
         if (rest <= 0) break;
-        double* panel = Bm + (long)(k0 + NB) * ldb + k0;
-        // L21 = A21 . L11^-T : C[m, n] = sum_k A21[m, k] * Linv[n, k]   (in place: one CTA owns whole rows)
-        gemm::TaskBatch b1;
-        b1.n = 1;
-        b1.t[0] = make_task(panel, ldb, linv, NB, nullptr, 0, panel, ldb, rest, NB, NB, 1.0, 0.0, 0);
-        e = gemm::launch(b1, gemm::B_T, s);
-        if (e != cudaSuccess) return e;
-        // A22 -= L21 . L21^T  (lower tiles only)
-        double* trail = Bm + (long)(k0 + NB) * ldb + (k0 + NB);
+        // trailing update once per outer block: A22 -= L[o1:, o0:o1] . L[o1:, o0:o1]^T  (lower tiles only), K = o1 - o0
+        double* lp = Bm + (long)o1 * ldb + o0;
+        double* trail = Bm + (long)o1 * ldb + o1;
         gemm::TaskBatch b2;
         b2.n = 1;
-        b2.t[0] = make_task(panel, ldb, panel, ldb, trail, ldb, trail, ldb, rest, rest, NB, -1.0, 1.0, 1);
+        b2.t[0] = make_task(lp, ldb, lp, ldb, trail, ldb, trail, ldb, rest, rest, o1 - o0, -1.0, 1.0, 1);
         e = gemm::launch(b2, gemm::B_T, s);
         if (e != cudaSuccess) return e;
     }

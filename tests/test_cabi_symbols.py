@@ -75,3 +75,14 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_library_has_no_unresolved_internal_symbols():
+    """nvcc -shared links happily with undefined references; make sure every internal entry point (chol_*, ozaki_*, refine_*,
+    gemm::, launch_*, comm_*) that some object file calls is actually defined in the library."""
+    import subprocess
+    from geobo_b200.csrc import build as b
+    lib = b.build()
+    out = subprocess.run(["nm", "-D", "--undefined-only", lib], capture_output=True, text=True).stdout
+    bad = [ln for ln in out.splitlines() if any(k in ln for k in ("chol_", "ozaki", "refine_", "gemm", "launch_", "comm_", "gb_"))]
+    assert not bad, bad
