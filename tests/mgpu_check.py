@@ -1,5 +1,5 @@
 """Multi-GPU parity check; run under torchrun (one rank per GPU):
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/mgpu_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_check.py
 Every rank runs Inversion.cubing on its voxel-column shard; rank 0 compares the gathered cubes with the CPU oracle."""
 import os
 import sys

@@ -20,7 +20,7 @@ def test_two_rank_sharded_inversion_matches_oracle(dist_chol):
         pytest.skip("needs 2 GPUs")
     port = 29600 + os.getpid() % 300 + int(dist_chol)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tools", "mgpu_check.py")]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, GEOBO_B200_DIST_CHOL=dist_chol))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MGPU_OK world=2" in r.stdout

@@ -1,0 +1,125 @@
+"""Parity at BASELINE's full sizes against results of the CPU oracle computed in full.
+
+``tests/golden/fullsize_cfg2.npz`` (32x32x32, exp, nd = 0, M = 2048) and ``fullsize_cfg3.npz`` (64x64x32, matern32 with
+scales L.[1, 1.01, 1.02], nd = 50, M = 8242) hold the inputs and every ``stride``-th voxel of the six result cubes of one
+complete oracle inversion (``tests/golden/make_fullsize_golden.py``, run once in the build container: 107 s / about
+1.5 h on 6-7 cores), plus max|cube| and sum(cube) over the full cubes.  The device path gets exactly the stored inputs
+through ``Inversion.cubing`` and must reproduce them within the tolerance the north star states: 1e-5 relative on
+posterior mean and variance (norm-wise per cube, max|delta| / max|ref|).  The measured errors are written to
+``gpurun_out/fullsize_parity.json`` when that directory is writable.
+
+The file sorts last on purpose: these are the longest GPU tests (the fp64 path needs about half a minute per 64x64x32
+inversion).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CUBES, GOLDEN, ROOT, load_golden
+from oracle import numpy_oracle as o
+
+TOL_STATED = 1e-5
+
+
+def _have(name):
+    return os.path.exists(os.path.join(GOLDEN, "fullsize_%s.npz" % name))
+
+
+def _inputs(g):
+    cfg = json.loads(str(g["cfg"]))
+    xN, yN, zN = cfg["xNcube"], cfg["yNcube"], cfg["zNcube"]
+    d0 = np.zeros(xN * yN * zN)
+    d0[g["didx"]] = g["drillvals"]
+    d0 = d0.reshape(xN, yN, zN)
+    return cfg, d0
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_fullsize_fixture_is_what_the_generator_describes(name):
+    """CPU: provenance of the fixture -- the stored surveys are the oracle's forward simulation of the bench's truth
+    cube (checked on a few sensors), the drill values sit on the drilled voxels, the sub-sampled cubes have the
+    documented length and stay inside the stored maxima."""
+    if not _have(name):
+        pytest.skip("fixture fullsize_%s.npz not generated" % name)
+    from geobo_b200 import config_loader, synth
+    g = load_golden("fullsize_%s.npz" % name)
+    cfg, d0 = _inputs(g)
+    config_loader.load_settings(cfg, make_outpath=False)
+    c = o.make_config(cfg)
+    N, Ns = c.xNcube * c.yNcube * c.zNcube, c.xNcube * c.yNcube
+    E, vp = o.cube_geometry(c)
+    dens, mags = synth.cylinders(vp)
+    rows = [0, Ns // 3, Ns - 1]
+    loc = o.sensor_grid(c)
+    Ag = o.a_sens(c, c.magneticField * 0, loc, E, "grav", sensors=rows)
+    Am = o.a_sens(c, c.magneticField, loc, E, "magn", sensors=rows)
+    assert np.allclose((Ag @ dens.ravel()).astype(np.float32), g["grav"][rows], rtol=1e-6)
+    assert np.allclose((Am @ mags.ravel()).astype(np.float32), g["mag"][rows], rtol=1e-6)
+    assert g["grav"].shape == g["mag"].shape == (Ns,)
+    assert np.array_equal(dens.ravel()[g["didx"]], g["drillvals"]) and (g["drillvals"] != 0).all()
+    stride = int(g["stride"])
+    for n in CUBES:
+        sub = g["sub_" + n]
+        assert sub.shape == (len(range(0, N, stride)),)
+        if g["didx"].size == 0 and n.startswith("drill"):
+            assert np.isnan(sub).all()              # no drill data -> NaN cubes (Q9)
+        else:
+            assert np.isfinite(sub).all() and np.abs(sub).max() <= float(g["max_" + n])
+    for n in ("density_var", "magsus_var"):
+        assert g["sub_" + n].min() > 0.0            # posterior variance stays positive at full size
+    cpu = json.loads(str(g["cpu"]))
+    assert cpu["wall_s"] > 0 and set(cpu["core_seconds_per_stage"]) >= {"kernel_eval", "dgemm_proj", "chol", "trsm"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,prec", [("cfg2", "fp64"), ("cfg2", "int8x5"), ("cfg3", "int8x5"), ("cfg3", "fp64")])
+def test_fullsize_cubing_vs_cpu_oracle(name, prec):
+    if not _have(name):
+        pytest.skip("fixture fullsize_%s.npz not generated" % name)
+    from geobo_b200 import _lib, config_loader, inversion
+    g = load_golden("fullsize_%s.npz" % name)
+    cfg, d0 = _inputs(g)
+    cfg["precision"] = prec
+    config_loader.load_settings(cfg, make_outpath=False)
+    c = o.make_config(cfg)
+    N = c.xNcube * c.yNcube * c.zNcube
+    inv = inversion.Inversion()
+    inv.create_cubegeometry()
+    inv.gp_length = np.array(g["gl0"], dtype=float)
+    try:
+        out = inv.cubing(g["grav"], g["mag"], d0[d0 != 0], o.sensor_grid(c), d0)
+    finally:
+        if inv._problem is not None:
+            inv._problem.close()
+            inv._problem = None
+        _lib.default_context().release_cache()      # the next case has another size: give the cached buffers back
+    stride = int(g["stride"])
+    errs = {}
+    for n, cube in zip(CUBES, out):
+        assert cube.shape == (c.yNcube, c.xNcube, c.zNcube)
+        sub, ref_max = g["sub_" + n], float(g["max_" + n])
+        got = np.asarray(cube).ravel()
+        if np.isnan(sub).all():
+            assert np.isnan(got).all(), n
+            continue
+        assert np.isfinite(got).all(), n
+        errs[n] = float(np.abs(got[::stride] - sub).max() / ref_max)
+        # aggregates over the FULL cube (every voxel enters): the maximum and the sum
+        errs[n + "_max"] = abs(float(np.abs(got).max()) - ref_max) / ref_max
+        errs[n + "_sum"] = abs(float(got.sum()) - float(g["sum_" + n])) / (N * ref_max)
+    errs["logl_rel"] = abs(inv.logl - float(g["logl"])) / abs(float(g["logl"]))
+    try:
+        p = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(p, exist_ok=True)
+        path = os.path.join(p, "fullsize_parity.json")
+        allr = json.load(open(path)) if os.path.exists(path) else {}
+        allr["%s_%s" % (name, prec)] = errs
+        json.dump(allr, open(path, "w"), indent=1)
+    except Exception:
+        pass
+    worst = max(v for k, v in errs.items() if k != "logl_rel")
+    assert worst < TOL_STATED, errs
+    assert errs["logl_rel"] < (1e-6 if prec == "fp64" else 1e-4), errs
+    assert np.allclose(inv.gp_length, g["gl_after"])
