@@ -67,6 +67,7 @@ _SIGNATURES = {
     "gb_forward": (C.c_int, [_P, C.c_int, _P, _P]),
     "gb_acquisition_vertical": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, C.c_double, _P]),
     "gb_acquisition_drill": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _P, C.c_int64, C.c_double, C.c_double, _P]),
+    "gb_align_drill": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int64, _P, _P]),
     "gb_posterior_cov": (C.c_int, [_P, C.POINTER(Hyper), _P]),
     "gb_get_timings": (C.c_int, [_P, _P, C.c_int]),
     "gb_problem_device_bytes": (C.c_uint64, [_P]),
@@ -165,6 +166,21 @@ class Context:
         out = np.empty(prm.shape[0])
         self.check(self.lib.gb_acquisition_drill(self.h, _ptr(rec), _ptr(var), _ptr(cst) if cst is not None else None, _ptr(shp), _ptr(vs),
                                                  float(zmax), float(length), _ptr(prm), int(prm.shape[0]), float(kappa), float(beta), _ptr(out)))
+        return out
+
+    # ---- geobo/run_geobo.py drill data
+    def align_drill(self, voxelpos, coord, data, voxsize):
+        """Flat voxel cube (voxel order of ``voxelpos``, shape (3, N)) of the windowed sample means (run_geobo.py:132-159)."""
+        vp = _f64(voxelpos).reshape(3, -1)
+        cd = _f64(coord).reshape(-1, 3)
+        dv = _f64(data).ravel()
+        if dv.size != cd.shape[0]:
+            raise ValueError("align_drill: %d coordinates but %d data values" % (cd.shape[0], dv.size))
+        vs = _f64(voxsize)
+        out = np.empty(vp.shape[1])
+        ns = int(cd.shape[0])
+        self.check(self.lib.gb_align_drill(self.h, _ptr(vp), int(vp.shape[1]), _ptr(cd) if ns else None, _ptr(dv) if ns else None, ns,
+                                           _ptr(vs), _ptr(out)))
         return out
 
     def allgather(self, local):

@@ -182,6 +182,15 @@ int gb_acquisition_vertical(gb_ctx* ctx, const double* rec, const double* var, c
 int gb_acquisition_drill(gb_ctx* ctx, const double* rec, const double* var, const double* costs, const int64_t shape[3],
                          const double voxsize[3], double zmax, double length, const double* params, int64_t n, double kappa,
                          double beta, double* out);
+/* ------------------------------------------------------------------ geobo/run_geobo.py (drill data)
+ * align_drill (run_geobo.py:132-159; utils.align_drill2, utils.py:55-83): drill-core samples -> voxel cube.
+ *   voxelpos [3][n_vox]: voxel-centre coordinates as Inversion.create_cubegeometry returns them (rows x, y, z); the output
+ *   is flat in the same voxel order, so the caller reshapes it like the arrays xxx / yyy / zzz it would have passed;
+ *   coord [ns][3], data [ns]: sample positions (local coordinates) and values; voxsize = (xvoxsize, yvoxsize, zvoxsize).
+ *   out[v] = mean of the non-NaN samples with  centre - voxsize <= coordinate < centre + voxsize  on all three axes (a
+ *   window of two voxel sizes, as coded), 0 where there is no such sample or the mean is not finite.  ns may be 0. */
+int gb_align_drill(gb_ctx* ctx, const double* voxelpos, int64_t n_vox, const double* coord, const double* data, int64_t ns,
+                   const double voxsize[3], double* out);
 /* Dense posterior covariance block (small cubes only; inversion.py:117): out (3N x 3N). */
 int gb_posterior_cov(gb_problem* p, const gb_hyper* h, double* out);
 int gb_get_timings(gb_problem* p, double* ms, int n);

@@ -557,3 +557,39 @@ def futility_drill(params, drill_rec, drill_var, kappa, beta, c, costs=None):
     except Exception:
         total = 0.
     return -total
+
+
+# ------------------------------------------------------------------------------------------------ drill voxelisation
+def _in_window(c, centre, half):
+    return (centre - half <= c) & (c < centre + half)
+
+
+def align_drill(coord, data, xxx, yyy, zzz, voxelsize):
+    """run_geobo.py:132-159 (utils.align_drill2, utils.py:55-83): per voxel the nanmean of the samples inside the half-open
+    window centre -/+ ONE VOXEL SIZE per axis; voxels without a finite mean keep 0.  Only voxels near some sample are
+    visited (the others cannot select anything); selection and mean are NumPy's own, as in the reference loop."""
+    import warnings
+    coord = np.asarray(coord, dtype=float).reshape(-1, 3)
+    data = np.asarray(data, dtype=float)
+    centres = (np.asarray(xxx, dtype=float), np.asarray(yyy, dtype=float), np.asarray(zzz, dtype=float))
+    res = np.zeros(centres[0].shape)
+    if coord.shape[0] == 0:
+        return res
+    near = np.zeros(res.shape, dtype=bool)
+    for lo in range(0, coord.shape[0], 256):
+        close = np.ones(res.shape + (min(256, coord.shape[0] - lo),), dtype=bool)
+        for ax in range(3):
+            close &= np.abs(centres[ax][..., None] - coord[lo:lo + 256, ax]) <= voxelsize[ax]
+        near |= close.any(axis=-1)
+    for idx in zip(*np.nonzero(near)):
+        sel = np.ones(coord.shape[0], dtype=bool)
+        for ax in range(3):
+            sel &= _in_window(coord[:, ax], centres[ax][idx], voxelsize[ax])
+        picked = data[np.where(sel)]
+        if picked.size:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")            # "Mean of empty slice" for all-NaN selections
+                m = np.nanmean(picked)
+            if np.isfinite(m):
+                res[idx] = m
+    return res
