@@ -593,3 +593,53 @@ def align_drill(coord, data, xxx, yyy, zzz, voxelsize):
             if np.isfinite(m):
                 res[idx] = m
     return res
+
+
+# ------------------------------------------------------------------------------------------------ simulator
+def _binarise_top_decile(layer):
+    """simcube.py:58-60: values below the 90th percentile -> 0, the rest -> the maximum."""
+    cut = np.percentile(layer, 90)
+    layer[layer < cut] = 0.0
+    layer[layer >= cut] = layer.max()
+    return layer
+
+
+def syncube(c, modelname, voxelpos):
+    """simcube.create_syncube (simcube.py:34-94) without the file output: density and susceptibility cubes (yN, xN, zN) of
+    the models 'cylinders', 'layers_2', 'layers_3' as functions of the voxel-centre coordinates."""
+    shp = (c.yNcube, c.xNcube, c.zNcube)
+    x3, y3, z3 = (np.asarray(v).reshape(shp) for v in voxelpos)
+    if modelname == "cylinders":
+        density, _ = cylinders_truth(c, voxelpos)
+    elif modelname in ("layers_2", "layers_3"):
+        # the dip of the layers along y; 'layers_2' centres it on zLcube / 2 (simcube.py:56), 'layers_3' on yLcube / 2 (:68)
+        mid = c.zLcube / 2 if modelname == "layers_2" else c.yLcube / 2.0
+        with np.errstate(over="ignore"):
+            zshift = c.zLcube / 8.0 * 1.0 / (1 + np.exp(2.0 * (-y3 + mid)))
+        bands = {}
+        for name, amp, top, bottom in (("l3", 6.0, 0.35, 0.375), ("l1", 4.0, 0.3, 0.325), ("l2", 8.0, 0.25, 0.275)):
+            if name == "l3" and modelname == "layers_2":
+                continue
+            # one layer: amp * (S(u_top) - S(u_bottom)), S(u) = 1 / (1 + exp(-2u)), u = -z - zLcube * fraction + zshift
+            with np.errstate(over="ignore"):
+                bands[name] = _binarise_top_decile(amp * (1.0 / (1 + np.exp(-2 * (-z3 - c.zLcube * top + zshift)))
+                                                         - 1.0 / (1 + np.exp(-2 * (-z3 - c.zLcube * bottom + zshift)))))
+        density = 0.5 + bands["l1"] + bands["l2"]
+        if modelname == "layers_3":
+            density = density + bands["l3"]
+    else:
+        raise ValueError("unknown model %r" % modelname)
+    return density, c.gp_coeff[1] * density
+
+
+def synsurvey(c, density, magsus):
+    """simcube.create_synsurvey (simcube.py:119-159) without the file output: sensors over the voxel-column centres at
+    height zoff, gravity = A_grav . density, magnetic = A_magn . magsus; returns the two (yN, xN) maps and the locations."""
+    Edges, _ = cube_geometry(c)
+    xs = np.arange(c.xvoxsize / 2.0, c.xLcube + c.xvoxsize / 2.0, c.xvoxsize)
+    ys = np.arange(c.yvoxsize / 2.0, c.yLcube + c.yvoxsize / 2.0, c.yvoxsize)
+    xx, yy = np.meshgrid(xs, ys)
+    loc = np.asarray([xx.flatten(), yy.flatten(), (xx * 0.0 + c.zoff).flatten()]).T
+    grav = a_sens(c, c.magneticField * 0.0, loc, Edges, "grav") @ np.asarray(density).flatten()
+    mag = a_sens(c, c.magneticField, loc, Edges, "magn") @ np.asarray(magsus).flatten()
+    return grav.reshape(xx.shape), mag.reshape(xx.shape), loc
