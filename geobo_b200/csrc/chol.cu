@@ -228,6 +228,15 @@ static gemm::Task make_task(const double* A, long lda, const double* B, long ldb
     return t;
 }
 
+// GEOBO_B200_CHOL_OUTER = panels per outer block (1 = plain right-looking, the default; 4 = two-level blocking: the
+// panels of a 512-wide block are factored left-looking and the trailing matrix is updated once per block with K = 512,
+// which keeps the DMMA pipe busier than four K = 128 updates).  Read on every call (tests switch it in-process).
+static int chol_outer_panels() {
+    int outer = 1;
+    if (const char* ev = getenv("GEOBO_B200_CHOL_OUTER")) { outer = atoi(ev); if (outer < 1 || outer > 16) outer = 1; }
+    return outer;
+}
+
 cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, cudaStream_t s) {
     static bool attr_set = false;
     const int smem = (NB * PLD + 64 * 64 + NB) * (int)sizeof(double);
@@ -238,11 +247,7 @@ cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork&
         attr_set = true;
     }
     const int nblk = Mp / NB;
-    // GEOBO_B200_CHOL_OUTER = panels per outer block (1 = plain right-looking, the default; 4 = two-level blocking: the
-    // panels of a 512-wide block are factored left-looking and the trailing matrix is updated once per block with K = 512,
-    // which keeps the DMMA pipe busier than four K = 128 updates)
-    int outer = 1;
-    if (const char* ev = getenv("GEOBO_B200_CHOL_OUTER")) { outer = atoi(ev); if (outer < 1 || outer > 16) outer = 1; }
+    const int outer = chol_outer_panels();
     for (int ob = 0; ob < nblk; ob += outer) {
         const int o0 = ob * NB, oe = (ob + outer < nblk ? ob + outer : nblk), o1 = oe * NB;
         for (int kb = ob; kb < oe; ++kb) {
@@ -339,11 +344,24 @@ int chol_factor_dist(gb_ctx* ctx, double* Bm, long ldb, int Mp, int Mtrue, const
     const int nblk = Mp / NB, nr = ctx->nranks, me = ctx->rank;
     GB_CUDA(ctx, cudaMemsetAsync(pan, 0, (size_t)2 * nblk * sizeof(double), s));
     GB_CUDA(ctx, cudaMemsetAsync(paninfo, 0, (size_t)nblk * sizeof(int), s));
+    // Two-level blocking (GEOBO_B200_CHOL_OUTER = panels per outer block > 1): inside an outer block the owner of a panel
+    // first applies the earlier panels of that block to its own column block (left-looking, operands from its replica of
+    // L, which the unpack below keeps complete), and the trailing column blocks are updated once per outer block with
+    // K = outer x 128 instead of once per panel with K = 128.  Same flops per rank, fatter GEMMs.
+    const int outer = chol_outer_panels();
     for (int kb = 0; kb < nblk; ++kb) {
         const int k0 = kb * NB, rows = Mp - k0, owner = kb % nr;
+        const int ob = kb / outer * outer, o0 = ob * NB, oe = ob + outer < nblk ? ob + outer : nblk, o1 = oe * NB;
         double* linv = w.linv + (long)kb * NB * NB;
         const long count = (long)rows * NB + NB * NB;
         if (me == owner) {
+            if (outer > 1 && k0 > o0) {
+                double* c = Bm + (long)k0 * ldb + k0;
+                gemm::TaskBatch b0;
+                b0.n = 1;
+                b0.t[0] = make_task(Bm + (long)k0 * ldb + o0, ldb, Bm + (long)k0 * ldb + o0, ldb, c, ldb, c, ldb, Mp - k0, NB, k0 - o0, -1.0, 1.0, 0);
+                GB_CUDA(ctx, gemm::launch(b0, gemm::B_T, s));
+            }
             potrf128_kernel<<<1, 256, smem, s>>>(Bm, ldb, k0, Mtrue, linv, pan + kb, paninfo + kb);
             GB_CUDA(ctx, cudaGetLastError());
             if (rows > NB) {
@@ -361,18 +379,34 @@ int chol_factor_dist(gb_ctx* ctx, double* Bm, long ldb, int Mp, int Mtrue, const
             panel_unpack_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(Bm, ldb, k0, rows, linv, stage);
             GB_CUDA(ctx, cudaGetLastError());
         }
-        // trailing update of the column blocks this rank owns: A[j0:, jb] -= L[j0:, kb] . L[jb rows, kb]^T, operands from the packed panel
         gemm::TaskBatch b2;
         b2.n = 0;
-        for (int jb = kb + 1; jb < nblk; ++jb) {
-            if (jb % nr != me) continue;
-            const int j0 = jb * NB;
-            const double* pj = stage + (long)(j0 - k0) * NB;          // rows j0.. of the packed panel (ld = NB)
-            double* c = Bm + (long)j0 * ldb + j0;
-            b2.t[b2.n++] = make_task(pj, NB, pj, NB, c, ldb, c, ldb, Mp - j0, NB, NB, -1.0, 1.0, 0);
-            if (b2.n == gemm::MAX_TASKS) {
-                GB_CUDA(ctx, gemm::launch(b2, gemm::B_T, s));
-                b2.n = 0;
+        if (outer == 1) {
+            // trailing update of the column blocks this rank owns: A[j0:, jb] -= L[j0:, kb] . L[jb rows, kb]^T, operands from the packed panel
+            for (int jb = kb + 1; jb < nblk; ++jb) {
+                if (jb % nr != me) continue;
+                const int j0 = jb * NB;
+                const double* pj = stage + (long)(j0 - k0) * NB;          // rows j0.. of the packed panel (ld = NB)
+                double* c = Bm + (long)j0 * ldb + j0;
+                b2.t[b2.n++] = make_task(pj, NB, pj, NB, c, ldb, c, ldb, Mp - j0, NB, NB, -1.0, 1.0, 0);
+                if (b2.n == gemm::MAX_TASKS) {
+                    GB_CUDA(ctx, gemm::launch(b2, gemm::B_T, s));
+                    b2.n = 0;
+                }
+            }
+        } else if (kb == oe - 1) {
+            // last panel of the outer block: A[j0:, jb] -= L[j0:, o0:o1] . L[jb rows, o0:o1]^T for the owned column blocks behind it,
+            // operands from this rank's replica of L (K = o1 - o0)
+            for (int jb = oe; jb < nblk; ++jb) {
+                if (jb % nr != me) continue;
+                const int j0 = jb * NB;
+                const double* lj = Bm + (long)j0 * ldb + o0;
+                double* c = Bm + (long)j0 * ldb + j0;
+                b2.t[b2.n++] = make_task(lj, ldb, lj, ldb, c, ldb, c, ldb, Mp - j0, NB, o1 - o0, -1.0, 1.0, 0);
+                if (b2.n == gemm::MAX_TASKS) {
+                    GB_CUDA(ctx, gemm::launch(b2, gemm::B_T, s));
+                    b2.n = 0;
+                }
             }
         }
         if (b2.n) GB_CUDA(ctx, gemm::launch(b2, gemm::B_T, s));

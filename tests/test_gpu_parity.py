@@ -210,6 +210,19 @@ def test_cubing_odd_shapes_vs_oracle(ctx, shape, kf, nd):
     assert abs(inv.logl - ex["logl"]) < 1e-7 * abs(ex["logl"])
 
 
+def test_two_level_cholesky_flag_vs_oracle(ctx, monkeypatch):
+    """GEOBO_B200_CHOL_OUTER=4: the panels of a 512-wide block are factored left-looking and the trailing matrix is
+    updated once per block (K = 512).  M = 1155 -> 10 panels = two full outer blocks and a ragged one of two panels."""
+    c = configure(base_cfg(), xNcube=24, yNcube=24, zNcube=4, kernelfunc="exp")
+    f = synthetic_inputs(c, 3)
+    ref, ex = o.cubing_lean(c, f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"])
+    monkeypatch.setenv("GEOBO_B200_CHOL_OUTER", "4")
+    inv, out = run_cubing(f)
+    for n, a, r in zip(CUBES, out, ref):
+        assert normwise_err(a, r) < TOL_CUBE, n
+    assert abs(inv.logl - ex["logl"]) < 1e-7 * abs(ex["logl"])
+
+
 def test_not_positive_definite_exits_like_reference(ctx, capsys):
     """matern32 with equal scales: 0/0 in the cross term -> Cholesky fails -> two prints + sys.exit(1) (inversion.py:99-104)."""
     c = configure(base_cfg(), xNcube=6, yNcube=5, zNcube=4, kernelfunc="matern32")
