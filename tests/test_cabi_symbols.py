@@ -86,3 +86,27 @@ def test_library_has_no_unresolved_internal_symbols():
     out = subprocess.run(["nm", "-D", "--undefined-only", lib], capture_output=True, text=True).stdout
     bad = [ln for ln in out.splitlines() if any(k in ln for k in ("chol_", "ozaki", "refine_", "gemm", "launch_", "comm_", "gb_"))]
     assert not bad, bad
+
+
+def test_null_handles_are_rejected_before_any_device_work(lib_path):
+    """Error behaviour of the boundary (include/geobo_b200.h conventions): every entry point that takes a context or a
+    problem returns GB_ERR_ARG for a NULL handle -- checked before any CUDA call, so this runs without a GPU -- and the
+    context-level ones leave their message in gb_last_error(NULL)."""
+    from geobo_b200 import _lib
+    lib = _lib.load_library()
+    ok_on_null = {"gb_ctx_destroy": 0, "gb_problem_destroy": 0, "gb_problem_device_bytes": 0}      # documented no-ops
+    skipped = {"gb_version", "gb_last_error", "gb_ctx_create"}
+    checked = 0
+    for name, (res, argtypes) in sorted(_lib._SIGNATURES.items()):
+        if name in skipped:
+            continue
+        args = [None if (t is ctypes.c_void_p or t is ctypes.c_char_p or hasattr(t, "contents")) else t(0) for t in argtypes]
+        rc = getattr(lib, name)(*args)
+        if name in ok_on_null:
+            assert rc == ok_on_null[name], name
+        else:
+            assert rc == -1, "%s(NULL, ...) returned %r, expected GB_ERR_ARG" % (name, rc)
+            checked += 1
+    assert checked >= 20
+    assert lib.gb_ctx_create(0, None) == -1 and b"out is NULL" in lib.gb_last_error(None)
+    assert lib.gb_grid_points(None, None, None, None) == -1 and b"gb_grid_points" in lib.gb_last_error(None)
