@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/geobo_b200.h"
+#include "formulas.cuh"
 
 struct gb_ctx {
     int device = 0;
@@ -77,12 +78,7 @@ struct DevBuf {
 };
 
 // ---------------------------------------------------------------------------- covariance functions (cov.cu)
-struct CovParams {
-    int kernel_id;
-    double l[3];   // de-duplicated length scales
-    double w[3];   // w1 (0-2), w2 (1-2), w3 (0-1)
-    double amp;
-};
+// CovParams: formulas.cuh
 
 // ---------------------------------------------------------------------------- fp64 tensor-pipe GEMM engine (gemm_f64.cu)
 namespace gemm {

@@ -6,29 +6,7 @@
 // association order, and writes the voxel row coalesced.  fp64 is mandatory: the 1e6 m edge padding
 // (sensormodel.py:64-68) makes the corner differences catastrophically cancelling.
 #include "common.cuh"
-
-#define GB_ALONG_WAY 1e6
-
-__device__ __forceinline__ double grav_corner(double x, double y, double z) {   // sensormodel.py:107-110
-    const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
-    const double t1 = __dmul_rn(x, log(__dadd_rn(y, r)));
-    const double t2 = __dmul_rn(y, log(__dadd_rn(x, r)));
-    const double t3 = __dmul_rn(z, atan(__ddiv_rn(__dmul_rn(x, y), __dadd_rn(__dmul_rn(z, r), 1e-9))));
-    return __dsub_rn(__dadd_rn(t1, t2), t3);
-}
-
-__device__ __forceinline__ double magn_corner(double x, double y, double z, double bx, double by, double bz) {
-    // sensormodel.py:127-133
-    const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
-    const double normB = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz)));
-    const double a1 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, by), bz), log(__dadd_rn(x, r)));
-    const double a2 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, bz), bx), log(__dadd_rn(y, r)));
-    const double a3 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, by), bx), log(__dadd_rn(z, r)));
-    const double a4 = __dmul_rn(__dsub_rn(__dmul_rn(bz, bz), __dmul_rn(by, by)), atan(__ddiv_rn(__dmul_rn(x, z), __dmul_rn(y, r))));
-    const double a5 = __dmul_rn(__dsub_rn(__dmul_rn(bz, bz), __dmul_rn(bx, bx)), atan(__ddiv_rn(__dmul_rn(y, z), __dmul_rn(x, r))));
-    const double sum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(a1, a2), a3), a4), a5);
-    return -__dmul_rn(__ddiv_rn(1.0, normB), sum);
-}
+#include "formulas.cuh"
 
 template <int KIND>
 __global__ void __launch_bounds__(256) a_sens_kernel(const double* __restrict__ edges, const double* __restrict__ loc,
