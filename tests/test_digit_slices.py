@@ -80,3 +80,30 @@ def test_sliced_pipeline_error_model_vs_fp64_oracle(kf, S, tol_mu, tol_var):
     if S == 5:      # without refinement the mean carries the slice error of AkA and Pt
         mu0, _ = ds.predict_sliced([Ag, Am], didx, kcov, y, sig, amp, S, refine=0)
         assert np.abs(mu0 - mu_ref).max() >= np.abs(mu - mu_ref).max()
+
+
+def test_device_digit_extraction_source_equals_the_restatement(tmp_path):
+    """csrc/ozaki.cuh (ozaki::digits<S>, ozaki::scale_exp) compiled for the host: the bytes the device kernels would
+    write are the digits of ``ds.balanced_digits`` bit for bit, and the scaling exponents agree."""
+    import ctypes
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    so = tmp_path / "ozaki_host.so"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I" + cuda_inc,
+                    os.path.join(root, "tests", "host_harness", "ozaki_host.cpp"), "-o", str(so)], check=True)
+    lib = ctypes.CDLL(str(so))
+    lib.host_scale_exp.argtypes = [ctypes.c_double]
+    rng = np.random.default_rng(99)
+    t = np.concatenate([rng.uniform(-0.5, 0.5, 50000), [0.5, -0.5, 0.0, -0.0, 2.0**-60, -2.0**-60, 0.5 - 2.0**-50, -0.5 + 2.0**-53],
+                        np.ldexp(rng.uniform(-0.5, 0.5, 2000), rng.integers(-40, 0, 2000))])
+    t = np.ascontiguousarray(t)
+    for S in (4, 5, 6):
+        out = np.empty((t.size, S), dtype=np.uint8)
+        assert lib.host_digits(S, t.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(t.size), out.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert np.array_equal(out.view(np.int8).astype(np.int64), ds.balanced_digits(t, S)), S
+    for amax in [0.0, -1.0, np.nan, np.inf, 1.0, 0.5, 0.75, 1e-300, 3.7e5, 2.0**-20, np.nextafter(1.0, 0)]:
+        assert lib.host_scale_exp(amax) == ds.scale_exp(amax), amax
