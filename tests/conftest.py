@@ -15,6 +15,30 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs the reference tree at /root/reference (build container only)")
 
 
+# GPU tests written after the round's GPU minutes were spent have not run on hardware yet.  They are collected
+# AFTER the hardware-verified parity tests, so that under `-x` a surprise in new code cannot hide the parity result
+# of the path itself.  Drop a name from this list once a `gpurun` log under profiles/ shows it green.
+NOT_YET_RUN_ON_HARDWARE = (
+    "test_gpu_proposal_drivers_vs_oracle",
+    "test_gpu_align_drill_",
+    "test_our_arm_line",
+    "test_gpu_optimize_gp_",
+    "test_gpu_create_synsurvey_",
+    "test_two_level_cholesky_flag_vs_oracle",
+    "test_gpu_kron_",
+    "test_fullsize_cubing_vs_cpu_oracle",
+)
+
+
+def pytest_collection_modifyitems(config, items):
+    def rank(item):
+        for i, prefix in enumerate(NOT_YET_RUN_ON_HARDWARE):
+            if item.name.startswith(prefix):
+                return 1 + i
+        return 0
+    items.sort(key=rank)        # stable: file order is kept inside each group
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
