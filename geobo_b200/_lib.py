@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libgeobo_b200.so")
 
 GB_OK = 0
 KERNEL_IDS = {"sparse": 0, "exp": 1, "matern32": 2}
+STRUCTURE_IDS = {"dense": 0, "kron": 1}     # gb_hyper.structure (GB_STRUCTURE_*)
 SENS_KINDS = {"grav": 0, "magn": 1}
 FLAG_MEAN, FLAG_VAR, FLAG_LOGL, FLAG_ALL = 1, 2, 4, 7
 TIMER_NAMES = ["a_sens", "tables", "project", "drill_rows", "aka", "allreduce", "chol", "trsm", "mean_var", "total", "d2h", "launches"]
@@ -34,7 +35,7 @@ class ProblemDesc(C.Structure):
 
 class Hyper(C.Structure):
     _fields_ = [("gp_length", C.c_double * 3), ("gp_sigma", C.c_double * 3), ("coeffm", C.c_double * 3),
-                ("gp_amp", C.c_double), ("kernel_id", C.c_int), ("slices", C.c_int), ("refine", C.c_int)]
+                ("gp_amp", C.c_double), ("kernel_id", C.c_int), ("slices", C.c_int), ("refine", C.c_int), ("structure", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol here is declared in include/geobo_b200.h
@@ -301,7 +302,7 @@ class Problem:
         self.ctx.check(self.lib.gb_problem_set_data(self.h, _ptr(y)))
 
     @staticmethod
-    def hyper(gp_length, gp_sigma, coeffm, gp_amp, kernel, slices=0, refine=1):
+    def hyper(gp_length, gp_sigma, coeffm, gp_amp, kernel, slices=0, refine=1, structure="dense"):
         h = Hyper()
         h.gp_length[:] = [float(v) for v in gp_length]
         h.gp_sigma[:] = [float(v) for v in gp_sigma]
@@ -312,6 +313,9 @@ class Problem:
         h.kernel_id = KERNEL_IDS[kernel]
         h.slices = int(slices)
         h.refine = int(refine)
+        if structure not in STRUCTURE_IDS:
+            raise ValueError("structure must be one of %s, got %r" % (sorted(STRUCTURE_IDS), structure))
+        h.structure = STRUCTURE_IDS[structure]
         return h
 
     def predict(self, hyper, want_host=True, flags=FLAG_ALL):

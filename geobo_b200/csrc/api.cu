@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "kron.cuh"
 #include "comm.h"
 
 std::string g_gb_create_error;
@@ -346,6 +347,10 @@ struct gb_problem {
     double* rf_z = nullptr;              // [3][ncp]  K w on this rank's voxel columns
     double* rf_part = nullptr;           // [8][2][Kp]
     double* rf_t = nullptr;              // [Mp] x 3: t, r, tmp
+    // Kronecker-structured products (gb_hyper.structure = GB_STRUCTURE_KRON, exp kernel): factor lines and row-chunk scratch
+    double* kron_f = nullptr;            // [9][3][FL]
+    double* kron_T = nullptr;            // [3][chunk][nyl][xN * zN]
+    long kron_T_doubles = 0;
     long nlaunch = 0;
     double* y_host_pinned = nullptr;
     double* out_pinned = nullptr;        // [6*ncol + 4]
@@ -373,7 +378,7 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
     void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
                     p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp,
                     p->Linv, p->tmpL, p->alpha, p->l8, p->l_exp, p->b8, p->b_exp, p->partial,
-                    p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch, p->chol_stage, p->chol_pan, p->chol_paninfo,
+                    p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch, p->chol_stage, p->chol_pan, p->chol_paninfo, p->kron_f, p->kron_T,
                     p->linv, p->scal, p->info, p->mu, p->var};
     for (void* q : ptrs)
         if (q) gb_dev_free(p->ctx, q);
@@ -607,6 +612,25 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     GB_CUDA(ctx, launch_cov_tables(cp, p->n, p->vox, p->tables, s));
     GB_CUDA(ctx, cudaEventRecord(p->ev[1], s));
 
+    // ---- opt-in structure-exploiting path: factor lines of the separable exp blocks from the tables
+    const bool kron = h->structure == GB_STRUCTURE_KRON;
+    if (h->structure != GB_STRUCTURE_DENSE && !kron) return gb_fail(ctx, GB_ERR_ARG, "gb_hyper.structure must be GB_STRUCTURE_DENSE or GB_STRUCTURE_KRON; got %d", h->structure);
+    const KronGeom kg = kron_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1);
+    if (kron) {
+        if (h->kernel_id != GB_KERNEL_EXP)
+            return gb_fail(ctx, GB_ERR_UNSUPPORTED, "structure = kron needs kernelfunc 'exp': only the squared-exponential blocks (kernels.py:81-99) are "
+                           "Kronecker products on the voxel grid; use structure = dense");
+        char why[256];
+        if (!kron_supported(kg, why, sizeof why)) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "%s", why);
+        if (!p->kron_f) {
+            GB_CUDA(ctx, dev_alloc(p, &p->kron_f, (size_t)kron_factor_doubles(kg), false));
+            p->kron_T_doubles = kron_scratch_doubles(kg, Ns);
+            GB_CUDA(ctx, dev_alloc(p, &p->kron_T, (size_t)p->kron_T_doubles, false));
+        }
+        GB_CUDA(ctx, kron_build_factors(p->tables, p->ext, p->C0, kg, p->kron_f, s));
+        p->nlaunch += 1;
+    }
+
     // ---- Pt = A3 . K : fused assembly + projection, 6 (data block c, property block r) products
     if (h->slices != 0) {
         // int8 digit-slice products on tcgen05 / TMEM (ozaki.cu); everything downstream stays fp64
@@ -637,6 +661,14 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
             p->bytes += 2 * (size_t)ozaki_rows_bytes(Ns, p->Kp, S, ozaki_tile_np(S)) + p->b8_bytes;
             p->a8_slices = S;
         }
+    }
+    if (kron) {
+        // three Toeplitz mode products per block: rows of A_c -> y mode (scratch, L2 resident) -> z and x modes -> rows of Pt
+        for (int c = 0; c < 2; ++c)
+            GB_CUDA(ctx, kron_apply(kg, p->kron_f, c * 3, p->A[c], p->lda, Ns, p->kron_T, p->kron_T_doubles, p->Pt + (long)c * Ns * ldp, ldp, ncp,
+                                    0, s, &p->nlaunch));
+    } else if (h->slices != 0) {
+        const int S = h->slices;
         GB_CUDA(ctx, ozaki_slice_tables(p->tables, p->ext, S, p->t_exp, p->t8, s));
         OzakiArgs oa;
         oa.a8[0] = p->a8[0]; oa.a8[1] = p->a8[1]; oa.a_exp[0] = p->a_exp[0]; oa.a_exp[1] = p->a_exp[1];
@@ -780,8 +812,15 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         const int nref = h->refine < 0 ? 0 : h->refine;
         for (int itr = 0; itr <= nref; ++itr) {
             GB_CUDA(ctx, refine_at_alpha(ra, p->alpha, p->rf_w, s));       // w = A3^T alpha
-            GB_CUDA(ctx, refine_kw(ra, p->rf_w, p->rf_z, s));              // z = K w   (this rank's voxel columns)
-            p->nlaunch += 3 + (refine_kw_slices(ncol) > 1 ? 1 : 0) + (p->nd ? 1 : 0);
+            if (kron) {                                                    // z = K w   (this rank's voxel columns)
+                for (int c = 0; c < 3; ++c)                                // fixed order c = 0, 1, 2: deterministic sums
+                    GB_CUDA(ctx, kron_apply(kg, p->kron_f, c * 3, p->rf_w + (long)c * p->Kp, p->Kp, 1, p->kron_T, p->kron_T_doubles, p->rf_z, 0, ncp,
+                                            c > 0, s, &p->nlaunch));
+                p->nlaunch += 2 + (p->nd ? 1 : 0);
+            } else {
+                GB_CUDA(ctx, refine_kw(ra, p->rf_w, p->rf_z, s));
+                p->nlaunch += 3 + (refine_kw_slices(ncol) > 1 ? 1 : 0) + (p->nd ? 1 : 0);
+            }
             if (itr == nref) break;                                        // z = K A3^T alpha = posterior mean
             GB_CUDA(ctx, refine_a_z(ra, p->rf_z, rt, s));                  // t = A3 z  (partial over this rank's columns)
             GB_TRY(comm_allreduce_sum_f64(ctx, rt, (size_t)Mp));

@@ -182,6 +182,16 @@ cudaError_t refine_linv_t(const double* Linv, long Mp, const double* x, int xs, 
 cudaError_t refine_dot(const double* a, const double* b, long n, double* out, cudaStream_t s);
 cudaError_t refine_scatter_mu(const double* z, long ncp, long ncol, double* mu, cudaStream_t s);
 
+// Kronecker-structured products with the exp covariance blocks (kron.cu; opt-in, gb_hyper.structure = GB_STRUCTURE_KRON)
+struct KronGeom;
+long kron_factor_doubles(const KronGeom& g);
+long kron_scratch_doubles(const KronGeom& g, long rows);
+int kron_supported(const KronGeom& g, char* why, size_t len);
+cudaError_t kron_build_factors(const double* tables, long ext, long C0, const KronGeom& g, double* kf /*[9][3][FL]*/, cudaStream_t s);
+// out[s][r * r_stride_out + (j - c0)] (+)= sum_i A[s][i] * K_(blk0 + r)[i][j]  for rows s < nrows, r = 0..2, voxel columns j of the shard
+cudaError_t kron_apply(const KronGeom& g, const double* kf, int blk0, const double* A, long lda, long nrows, double* T, long T_doubles,
+                       double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch);
+
 // Cholesky / triangular solve (chol.cu)
 struct CholWork {
     double* linv = nullptr;   // [Mp/128][128][128] inverses of the diagonal blocks

@@ -86,11 +86,23 @@ class Inversion:
             return int(prec[-1])
         raise ValueError("settings key 'precision' must be 'fp64', 'int8x4', 'int8x5' or 'int8x6', got %r" % prec)
 
+    @staticmethod
+    def _structure():
+        """Optional settings key ``structure`` (absent in reference YAMLs -> 'dense'):
+        'dense' : the dense contraction ``Asens3 . kcov`` (``inversion.py:96,114``), any kernel;
+        'kron'  : for ``kernelfunc: 'exp'`` only -- on the voxel grid every block of ``create_cov`` (``kernels.py:81-99``)
+        is the Kronecker product of three small Toeplitz matrices, so the products with ``kcov`` run as three mode
+        products per block.  Same result to rounding; other kernels are refused by the library."""
+        st = str(getattr(_cfg, "structure", "dense")).lower()
+        if st not in _lib.STRUCTURE_IDS:
+            raise ValueError("settings key 'structure' must be 'dense' or 'kron', got %r" % st)
+        return st
+
     def _hyper(self, gp_length=None, coeffm=None, gp_amp=None):
         return _lib.Problem.hyper(self.gp_length if gp_length is None else gp_length, self.gp_sigma,
                                   self.coeffm if coeffm is None else coeffm,
                                   self.gp_amp if gp_amp is None else gp_amp, _cfg.kernelfunc, self._slices(),
-                                  int(getattr(_cfg, "refine", 1)))
+                                  int(getattr(_cfg, "refine", 1)), self._structure())
 
     def _build_problem(self):
         if not hasattr(self, "Edges"):

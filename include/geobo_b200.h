@@ -39,6 +39,10 @@ extern "C" {
 #define GB_KERNEL_EXP 1
 #define GB_KERNEL_MATERN32 2
 
+/* gb_hyper.structure */
+#define GB_STRUCTURE_DENSE 0
+#define GB_STRUCTURE_KRON 1
+
 /* forward-model kinds, geobo/sensormodel.py:71-74 */
 #define GB_SENS_GRAV 0
 #define GB_SENS_MAGN 1
@@ -149,6 +153,12 @@ typedef struct gb_hyper {
     int refine;                /* slices != 0 only: steps of iterative refinement of (A K A^T + Sigma)^-1 y against the fp64
                                   matrix-free operator before the mean K A3^T alpha is formed (0 = none; 1 is the default
                                   of the Python surface)                                                              */
+    int structure;             /* GB_STRUCTURE_DENSE (0, default): the dense contraction Pt = A3 . K the north star names;
+                                  GB_STRUCTURE_KRON (1): opt-in fast path for kernel_id = GB_KERNEL_EXP only -- on the regular
+                                  voxel grid every exp block of create_cov (kernels.py:81-99) is a Kronecker product
+                                  Ky (x) Kx (x) Kz, so Pt = A3 . K and the K . w of the refinement run as three Toeplitz mode
+                                  products (2 N (xN + yN + zN) flops per row instead of 2 N^2).  Any other
+                                  kernel is refused with GB_ERR_UNSUPPORTED.  Everything downstream is unchanged.           */
 } gb_hyper;
 
 /* Builds the device-resident problem: computes both sensitivity matrices on the GPU
