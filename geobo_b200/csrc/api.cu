@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "kron.cuh"
+#include "stencil.cuh"
 #include "comm.h"
 
 std::string g_gb_create_error;
@@ -613,9 +614,19 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     GB_CUDA(ctx, cudaEventRecord(p->ev[1], s));
 
     // ---- opt-in structure-exploiting path: factor lines of the separable exp blocks from the tables
-    const bool kron = h->structure == GB_STRUCTURE_KRON;
-    if (h->structure != GB_STRUCTURE_DENSE && !kron) return gb_fail(ctx, GB_ERR_ARG, "gb_hyper.structure must be GB_STRUCTURE_DENSE or GB_STRUCTURE_KRON; got %d", h->structure);
+    const bool kron = h->structure == GB_STRUCTURE_KRON, compact = h->structure == GB_STRUCTURE_COMPACT;
+    if (h->structure != GB_STRUCTURE_DENSE && !kron && !compact)
+        return gb_fail(ctx, GB_ERR_ARG, "gb_hyper.structure must be GB_STRUCTURE_DENSE, GB_STRUCTURE_KRON or GB_STRUCTURE_COMPACT; got %d", h->structure);
     const KronGeom kg = kron_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1);
+    const StencilGeom sg = stencil_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1, p->vox, h->gp_length);
+    if (compact && h->kernel_id != GB_KERNEL_SPARSE)
+        return gb_fail(ctx, GB_ERR_UNSUPPORTED, "structure = compact needs kernelfunc 'sparse': only the compact-support kernels (kernels.py:101-138) "
+                       "vanish outside a window of the voxel grid; use structure = dense");
+    // out[s][r * ncp + (j - c0)] (+)= sum_i A[s][i] K_(blk0 + r)[i][j] through the structured form of the blocks
+    auto apply_structured = [&](int blk0, const double* A, long lda, long nrows, double* out, long ldo, int accumulate) -> cudaError_t {
+        if (kron) return kron_apply(kg, p->kron_f, blk0, A, lda, nrows, p->kron_T, p->kron_T_doubles, out, ldo, ncp, accumulate, s, &p->nlaunch);
+        return stencil_apply(sg, p->tables + (long)blk0 * p->ext + p->C0, A, lda, nrows, out, ldo, ncp, accumulate, s, &p->nlaunch);
+    };
     if (kron) {
         if (h->kernel_id != GB_KERNEL_EXP)
             return gb_fail(ctx, GB_ERR_UNSUPPORTED, "structure = kron needs kernelfunc 'exp': only the squared-exponential blocks (kernels.py:81-99) are "
@@ -662,11 +673,10 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
             p->a8_slices = S;
         }
     }
-    if (kron) {
-        // three Toeplitz mode products per block: rows of A_c -> y mode (scratch, L2 resident) -> z and x modes -> rows of Pt
-        for (int c = 0; c < 2; ++c)
-            GB_CUDA(ctx, kron_apply(kg, p->kron_f, c * 3, p->A[c], p->lda, Ns, p->kron_T, p->kron_T_doubles, p->Pt + (long)c * Ns * ldp, ldp, ncp,
-                                    0, s, &p->nlaunch));
+    if (kron || compact) {
+        // kron: three Toeplitz mode products per block (rows of A_c -> y mode into the L2-resident scratch -> z and x modes -> rows of Pt)
+        // compact: tap sum over the support window of the compact kernels
+        for (int c = 0; c < 2; ++c) GB_CUDA(ctx, apply_structured(c * 3, p->A[c], p->lda, Ns, p->Pt + (long)c * Ns * ldp, ldp, 0));
     } else if (h->slices != 0) {
         const int S = h->slices;
         GB_CUDA(ctx, ozaki_slice_tables(p->tables, p->ext, S, p->t_exp, p->t8, s));
@@ -812,10 +822,9 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         const int nref = h->refine < 0 ? 0 : h->refine;
         for (int itr = 0; itr <= nref; ++itr) {
             GB_CUDA(ctx, refine_at_alpha(ra, p->alpha, p->rf_w, s));       // w = A3^T alpha
-            if (kron) {                                                    // z = K w   (this rank's voxel columns)
+            if (kron || compact) {                                         // z = K w   (this rank's voxel columns)
                 for (int c = 0; c < 3; ++c)                                // fixed order c = 0, 1, 2: deterministic sums
-                    GB_CUDA(ctx, kron_apply(kg, p->kron_f, c * 3, p->rf_w + (long)c * p->Kp, p->Kp, 1, p->kron_T, p->kron_T_doubles, p->rf_z, 0, ncp,
-                                            c > 0, s, &p->nlaunch));
+                    GB_CUDA(ctx, apply_structured(c * 3, p->rf_w + (long)c * p->Kp, p->Kp, 1, p->rf_z, 0, c > 0));
                 p->nlaunch += 2 + (p->nd ? 1 : 0);
             } else {
                 GB_CUDA(ctx, refine_kw(ra, p->rf_w, p->rf_z, s));

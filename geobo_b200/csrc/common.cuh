@@ -192,6 +192,11 @@ cudaError_t kron_build_factors(const double* tables, long ext, long C0, const Kr
 cudaError_t kron_apply(const KronGeom& g, const double* kf, int blk0, const double* A, long lda, long nrows, double* T, long T_doubles,
                        double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch);
 
+// Compact-support (stencil) products with the 'sparse' covariance blocks (stencil.cu; opt-in, GB_STRUCTURE_COMPACT)
+struct StencilGeom;
+cudaError_t stencil_apply(const StencilGeom& g, const double* tab0 /* tables + blk0 * ext + C0 */, const double* A, long lda, long nrows,
+                          double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch);
+
 // Cholesky / triangular solve (chol.cu)
 struct CholWork {
     double* linv = nullptr;   // [Mp/128][128][128] inverses of the diagonal blocks

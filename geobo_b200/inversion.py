@@ -92,10 +92,12 @@ class Inversion:
         'dense' : the dense contraction ``Asens3 . kcov`` (``inversion.py:96,114``), any kernel;
         'kron'  : for ``kernelfunc: 'exp'`` only -- on the voxel grid every block of ``create_cov`` (``kernels.py:81-99``)
         is the Kronecker product of three small Toeplitz matrices, so the products with ``kcov`` run as three mode
-        products per block.  Same result to rounding; other kernels are refused by the library."""
+        products per block (SURVEY.md 8(f) row 3).  Same result to rounding; other kernels are refused by the library;
+        'compact' : for ``kernelfunc: 'sparse'`` only -- the compact-support kernels (``kernels.py:101-138``) vanish beyond
+        their length scale, so the products with ``kcov`` run as a tap sum over the offsets inside the support."""
         st = str(getattr(_cfg, "structure", "dense")).lower()
         if st not in _lib.STRUCTURE_IDS:
-            raise ValueError("settings key 'structure' must be 'dense' or 'kron', got %r" % st)
+            raise ValueError("settings key 'structure' must be 'dense', 'kron' or 'compact', got %r" % st)
         return st
 
     def _hyper(self, gp_length=None, coeffm=None, gp_amp=None):

@@ -42,6 +42,7 @@ extern "C" {
 /* gb_hyper.structure */
 #define GB_STRUCTURE_DENSE 0
 #define GB_STRUCTURE_KRON 1
+#define GB_STRUCTURE_COMPACT 2
 
 /* forward-model kinds, geobo/sensormodel.py:71-74 */
 #define GB_SENS_GRAV 0
@@ -158,7 +159,10 @@ typedef struct gb_hyper {
                                   voxel grid every exp block of create_cov (kernels.py:81-99) is a Kronecker product
                                   Ky (x) Kx (x) Kz, so Pt = A3 . K and the K . w of the refinement run as three Toeplitz mode
                                   products (2 N (xN + yN + zN) flops per row instead of 2 N^2).  Any other
-                                  kernel is refused with GB_ERR_UNSUPPORTED.  Everything downstream is unchanged.           */
+                                  kernel is refused with GB_ERR_UNSUPPORTED.  Everything downstream is unchanged.
+                                  GB_STRUCTURE_COMPACT (2): opt-in fast path for kernel_id = GB_KERNEL_SPARSE only -- the compact
+                                  kernels (kernels.py:101-138) vanish beyond their length scale, so the same two products run as
+                                  a 3-D tap sum over the offsets inside the support (taps from the stationary tables).           */
 } gb_hyper;
 
 /* Builds the device-resident problem: computes both sensitivity matrices on the GPU
