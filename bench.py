@@ -183,7 +183,7 @@ def run_ours(args):
     xN, yN, zN = wl["shape"]
     cfg = synth.settings(xN, yN, zN, kernelfunc=wl["kernel"], precision=args.precision, refine=args.refine, structure=args.structure)
     config_loader.load_settings(cfg, make_outpath=False)
-    kron = args.structure in ("kron", "compact")        # the two opt-in structure-exploiting projections share the reporting below
+    kron = args.structure in ("kron", "compact", "fft")        # the two opt-in structure-exploiting projections share the reporting below
     slices = inversion.Inversion._slices()
     N, Ns, nd = xN * yN * zN, xN * yN, wl["nd"]
     f = synth.make_inputs(nd=nd, seed=0, ctx=ctx)
@@ -275,7 +275,9 @@ def run_ours(args):
         ach = kron_bytes / proj_s / 1e9
         roofline = {"kernel": ("kron_y_kernel + kron_zx_kernel (Pt = A3.K for the separable exp blocks: y mode into an L2-resident scratch, "
                                "z and x modes in shared memory; fp64 FMA)") if args.structure == "kron" else
-                              "stencil_kernel (Pt = A3.K for the compact-support blocks: tap sum over the support window; fp64 FMA)",
+                              "stencil_kernel (Pt = A3.K for the compact-support blocks: tap sum over the support window; fp64 FMA)"
+                              if args.structure == "compact" else
+                              "fft_pass_kernel (Pt = A3.K as zero-padded 3-D FFT convolutions with the stationary tables; fp64 radix-2 passes in shared memory)",
                     "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if hbm else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth measured on this pool)",
                     "algorithmic_bytes_per_step": kron_bytes, "ms_per_step": stage_ms["project"],
@@ -320,8 +322,9 @@ def run_ours(args):
            "config": {"workload": wl["name"], "workload_id": args.workload, "voxels": N, "sensors_per_survey": Ns, "drill_rows": nd,
                       "data_rows_M": M, "kernel": wl["kernel"], "precision": args.precision + (" + %d refinement step(s)" % args.refine if slices else ""),
                       "structure": ("%s: %s (opt-in fast path, SURVEY 8(f) row 3; not the dense contraction the headline is quoted on)"
-                                    % (args.structure, "separable exp blocks as Toeplitz mode products" if args.structure == "kron" else
-                                       "compact-support blocks as a tap sum over the support window")) if kron else "dense",
+                                    % (args.structure, {"kron": "separable exp blocks as Toeplitz mode products",
+                                                        "compact": "compact-support blocks as a tap sum over the support window",
+                                                        "fft": "block-Toeplitz blocks as zero-padded 3-D FFT convolutions"}[args.structure])) if kron else "dense",
                       "parallelism": "voxel-column shards of Pt x%d" % world,
                       "l2": "inputs larger than L2 (A and Pt are %.1f GB)" % (device_bytes / 1e9),
                       "device_bytes": device_bytes},
@@ -427,10 +430,10 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("GEOBO_B200_PRECISION", "int8x5"),
                     choices=["fp64", "int8x4", "int8x5", "int8x6"],
                     help="projection arithmetic: fp64 DMMA, or error-free int8 digit products on tcgen05 (31/39/47 bits)")
-    ap.add_argument("--structure", default=os.environ.get("GEOBO_B200_STRUCTURE", "dense"), choices=["dense", "kron", "compact"],
+    ap.add_argument("--structure", default=os.environ.get("GEOBO_B200_STRUCTURE", "dense"), choices=["dense", "kron", "compact", "fft"],
                     help="dense: the contraction Pt = A3.K the metric is quoted on (default); kron: separable exp blocks as mode products "
-                         "(exp workloads only); compact: tap sum over the support of the compact kernel (sparse workloads only); both "
-                         "reported separately")
+                         "(exp workloads only); compact: tap sum over the support of the compact kernel (sparse workloads only); fft: 3-D FFT "
+                         "convolutions (any kernel); all reported separately")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "kron.cuh"
 #include "stencil.cuh"
+#include "fftconv.cuh"
 #include "comm.h"
 
 std::string g_gb_create_error;
@@ -352,6 +353,11 @@ struct gb_problem {
     double* kron_f = nullptr;            // [9][3][FL]
     double* kron_T = nullptr;            // [3][chunk][nyl][xN * zN]
     long kron_T_doubles = 0;
+    // block-Toeplitz FFT products (GB_STRUCTURE_FFT): spectra of the 9 wrapped tables, twiddles, scratch lattices X, Y, Z
+    double* fft_W = nullptr;             // [9][Py * Px * Pz]
+    cplx* fft_tw = nullptr;              // [3][FFT_MAXP / 2]
+    cplx* fft_scratch = nullptr;
+    long fft_B = 0;                      // complex row pairs per chunk
     long nlaunch = 0;
     double* y_host_pinned = nullptr;
     double* out_pinned = nullptr;        // [6*ncol + 4]
@@ -379,7 +385,7 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
     void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
                     p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp,
                     p->Linv, p->tmpL, p->alpha, p->l8, p->l_exp, p->b8, p->b_exp, p->partial,
-                    p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch, p->chol_stage, p->chol_pan, p->chol_paninfo, p->kron_f, p->kron_T,
+                    p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch, p->chol_stage, p->chol_pan, p->chol_paninfo, p->kron_f, p->kron_T, p->fft_W, p->fft_tw, p->fft_scratch,
                     p->linv, p->scal, p->info, p->mu, p->var};
     for (void* q : ptrs)
         if (q) gb_dev_free(p->ctx, q);
@@ -614,9 +620,11 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     GB_CUDA(ctx, cudaEventRecord(p->ev[1], s));
 
     // ---- opt-in structure-exploiting path: factor lines of the separable exp blocks from the tables
-    const bool kron = h->structure == GB_STRUCTURE_KRON, compact = h->structure == GB_STRUCTURE_COMPACT;
-    if (h->structure != GB_STRUCTURE_DENSE && !kron && !compact)
-        return gb_fail(ctx, GB_ERR_ARG, "gb_hyper.structure must be GB_STRUCTURE_DENSE, GB_STRUCTURE_KRON or GB_STRUCTURE_COMPACT; got %d", h->structure);
+    const bool kron = h->structure == GB_STRUCTURE_KRON, compact = h->structure == GB_STRUCTURE_COMPACT, fft = h->structure == GB_STRUCTURE_FFT;
+    const bool structured = kron || compact || fft;
+    if (h->structure != GB_STRUCTURE_DENSE && !structured)
+        return gb_fail(ctx, GB_ERR_ARG, "gb_hyper.structure must be GB_STRUCTURE_DENSE, _KRON, _COMPACT or _FFT; got %d", h->structure);
+    const FftGeom fg = fft_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1);
     const KronGeom kg = kron_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1);
     const StencilGeom sg = stencil_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1, p->vox, h->gp_length);
     if (compact && h->kernel_id != GB_KERNEL_SPARSE)
@@ -625,6 +633,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     // out[s][r * ncp + (j - c0)] (+)= sum_i A[s][i] K_(blk0 + r)[i][j] through the structured form of the blocks
     auto apply_structured = [&](int blk0, const double* A, long lda, long nrows, double* out, long ldo, int accumulate) -> cudaError_t {
         if (kron) return kron_apply(kg, p->kron_f, blk0, A, lda, nrows, p->kron_T, p->kron_T_doubles, out, ldo, ncp, accumulate, s, &p->nlaunch);
+        if (fft) return fft_apply(fg, p->fft_W, p->fft_tw, blk0, A, lda, nrows, p->fft_scratch, p->fft_B, out, ldo, ncp, accumulate, s, &p->nlaunch);
         return stencil_apply(sg, p->tables + (long)blk0 * p->ext + p->C0, A, lda, nrows, out, ldo, ncp, accumulate, s, &p->nlaunch);
     };
     if (kron) {
@@ -640,6 +649,20 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         }
         GB_CUDA(ctx, kron_build_factors(p->tables, p->ext, p->C0, kg, p->kron_f, s));
         p->nlaunch += 1;
+    }
+    if (fft) {
+        char why[256];
+        if (!fft_supported(fg, why, sizeof why)) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "%s", why);
+        if (!p->fft_W) {
+            p->fft_B = fft_chunk_pairs(fg, Ns);
+            GB_CUDA(ctx, dev_alloc(p, &p->fft_W, (size_t)9 * fg.P3, false));
+            GB_CUDA(ctx, dev_alloc(p, &p->fft_tw, (size_t)3 * (FFT_MAXP / 2), false));
+            GB_CUDA(ctx, dev_alloc(p, &p->fft_scratch, (size_t)fft_scratch_cplx(fg, p->fft_B), false));
+            GB_CUDA(ctx, fft_build_twiddles(fg, p->fft_tw, s));
+            p->nlaunch += 3;
+        }
+        // spectra of the 9 wrapped tables (they change with the hyper-parameters): X, Y = the first two scratch lattices
+        GB_CUDA(ctx, fft_build_spectra(fg, p->tables, p->ext, p->C0, p->fft_tw, p->fft_scratch, p->fft_scratch + p->fft_B * fg.P3, p->fft_W, s, &p->nlaunch));
     }
 
     // ---- Pt = A3 . K : fused assembly + projection, 6 (data block c, property block r) products
@@ -673,7 +696,8 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
             p->a8_slices = S;
         }
     }
-    if (kron || compact) {
+    if (structured) {
+        // fft: zero-padded 3-D FFT convolutions with the stationary tables (any kernel)
         // kron: three Toeplitz mode products per block (rows of A_c -> y mode into the L2-resident scratch -> z and x modes -> rows of Pt)
         // compact: tap sum over the support window of the compact kernels
         for (int c = 0; c < 2; ++c) GB_CUDA(ctx, apply_structured(c * 3, p->A[c], p->lda, Ns, p->Pt + (long)c * Ns * ldp, ldp, 0));
@@ -822,7 +846,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         const int nref = h->refine < 0 ? 0 : h->refine;
         for (int itr = 0; itr <= nref; ++itr) {
             GB_CUDA(ctx, refine_at_alpha(ra, p->alpha, p->rf_w, s));       // w = A3^T alpha
-            if (kron || compact) {                                         // z = K w   (this rank's voxel columns)
+            if (structured) {                                              // z = K w   (this rank's voxel columns)
                 for (int c = 0; c < 3; ++c)                                // fixed order c = 0, 1, 2: deterministic sums
                     GB_CUDA(ctx, apply_structured(c * 3, p->rf_w + (long)c * p->Kp, p->Kp, 1, p->rf_z, 0, c > 0));
                 p->nlaunch += 2 + (p->nd ? 1 : 0);

@@ -13,8 +13,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["api.cu", "gemm_f64.cu", "cov.cu", "sens.cu", "chol.cu", "comm.cu", "ozaki.cu", "ozaki_gemm.cu", "refine.cu", "acq.cu", "drill.cu", "kron.cu", "stencil.cu"]
-HEADERS = ["common.cuh", "comm.h", "umma.cuh", "ozaki.cuh", "drill.cuh", "kron.cuh", "stencil.cuh", "formulas.cuh", os.path.join("..", "..", "include", "geobo_b200.h")]
+SOURCES = ["api.cu", "gemm_f64.cu", "cov.cu", "sens.cu", "chol.cu", "comm.cu", "ozaki.cu", "ozaki_gemm.cu", "refine.cu", "acq.cu", "drill.cu", "kron.cu", "stencil.cu", "fftconv.cu"]
+HEADERS = ["common.cuh", "comm.h", "umma.cuh", "ozaki.cuh", "drill.cuh", "kron.cuh", "stencil.cuh", "fftconv.cuh", "formulas.cuh", os.path.join("..", "..", "include", "geobo_b200.h")]
 LIB = os.path.join(PKG, "libgeobo_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

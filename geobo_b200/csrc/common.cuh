@@ -197,6 +197,18 @@ struct StencilGeom;
 cudaError_t stencil_apply(const StencilGeom& g, const double* tab0 /* tables + blk0 * ext + C0 */, const double* A, long lda, long nrows,
                           double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch);
 
+// Block-Toeplitz (FFT) products with the stationary covariance blocks (fftconv.cu; opt-in, GB_STRUCTURE_FFT, any kernel)
+struct FftGeom;
+struct cplx;
+int fft_supported(const FftGeom& g, char* why, size_t len);
+long fft_chunk_pairs(const FftGeom& g, long rows);
+long fft_scratch_cplx(const FftGeom& g, long B);
+cudaError_t fft_build_twiddles(const FftGeom& g, cplx* tw /*[3][FFT_MAXP / 2]: y, x, z*/, cudaStream_t s);
+cudaError_t fft_build_spectra(const FftGeom& g, const double* tables, long ext, long C0, const cplx* tw, cplx* X, cplx* Y, double* W /*[9][P3]*/,
+                              cudaStream_t s, long* nlaunch);
+cudaError_t fft_apply(const FftGeom& g, const double* W, const cplx* tw, int blk0, const double* A, long lda, long nrows, cplx* scratch, long B,
+                      double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch);
+
 // Cholesky / triangular solve (chol.cu)
 struct CholWork {
     double* linv = nullptr;   // [Mp/128][128][128] inverses of the diagonal blocks

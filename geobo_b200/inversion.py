@@ -94,10 +94,12 @@ class Inversion:
         is the Kronecker product of three small Toeplitz matrices, so the products with ``kcov`` run as three mode
         products per block (SURVEY.md 8(f) row 3).  Same result to rounding; other kernels are refused by the library;
         'compact' : for ``kernelfunc: 'sparse'`` only -- the compact-support kernels (``kernels.py:101-138``) vanish beyond
-        their length scale, so the products with ``kcov`` run as a tap sum over the offsets inside the support."""
+        their length scale, so the products with ``kcov`` run as a tap sum over the offsets inside the support;
+        'fft'   : any kernel -- every block of ``create_cov`` is block-Toeplitz on the voxel grid, so the products with
+        ``kcov`` run as zero-padded 3-D FFT convolutions with the block's values on the offset lattice (fp64)."""
         st = str(getattr(_cfg, "structure", "dense")).lower()
         if st not in _lib.STRUCTURE_IDS:
-            raise ValueError("settings key 'structure' must be 'dense', 'kron' or 'compact', got %r" % st)
+            raise ValueError("settings key 'structure' must be 'dense', 'kron', 'compact' or 'fft', got %r" % st)
         return st
 
     def _hyper(self, gp_length=None, coeffm=None, gp_amp=None):

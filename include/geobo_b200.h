@@ -43,6 +43,7 @@ extern "C" {
 #define GB_STRUCTURE_DENSE 0
 #define GB_STRUCTURE_KRON 1
 #define GB_STRUCTURE_COMPACT 2
+#define GB_STRUCTURE_FFT 3
 
 /* forward-model kinds, geobo/sensormodel.py:71-74 */
 #define GB_SENS_GRAV 0
@@ -162,7 +163,10 @@ typedef struct gb_hyper {
                                   kernel is refused with GB_ERR_UNSUPPORTED.  Everything downstream is unchanged.
                                   GB_STRUCTURE_COMPACT (2): opt-in fast path for kernel_id = GB_KERNEL_SPARSE only -- the compact
                                   kernels (kernels.py:101-138) vanish beyond their length scale, so the same two products run as
-                                  a 3-D tap sum over the offsets inside the support (taps from the stationary tables).           */
+                                  a 3-D tap sum over the offsets inside the support (taps from the stationary tables).
+                                  GB_STRUCTURE_FFT (3): opt-in fast path for ANY kernel -- every block of create_cov is block-Toeplitz
+                                  on the voxel grid, so the same two products run as zero-padded 3-D FFT convolutions with the
+                                  stationary tables (circulant embedding, fp64, exact up to rounding).                        */
 } gb_hyper;
 
 /* Builds the device-resident problem: computes both sensitivity matrices on the GPU

@@ -27,6 +27,7 @@ NOT_YET_RUN_ON_HARDWARE = (
     "test_two_level_cholesky_flag_vs_oracle",
     "test_gpu_kron_",
     "test_gpu_compact_",
+    "test_gpu_fft_",
     "test_fullsize_cubing_vs_cpu_oracle",
 )
 

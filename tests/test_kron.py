@@ -147,11 +147,11 @@ def test_host_compiled_kernels_zero_block(host):
 
 def test_structure_key_is_validated():
     from geobo_b200 import _lib, config_loader, inversion
-    config_loader.load_settings(_cfg((4, 4, 4), structure="fft"), make_outpath=False)
+    config_loader.load_settings(_cfg((4, 4, 4), structure="wavelet"), make_outpath=False)
     with pytest.raises(ValueError, match="structure"):
         inversion.Inversion()._structure()
     with pytest.raises(ValueError, match="structure"):
-        _lib.Problem.hyper([1, 1, 1], [1, 1, 1], [1, 1, 1], 1.0, "exp", structure="fft")
+        _lib.Problem.hyper([1, 1, 1], [1, 1, 1], [1, 1, 1], 1.0, "exp", structure="wavelet")
     h = _lib.Problem.hyper([1, 1, 1], [1, 1, 1], [1, 1, 1], 1.0, "exp", structure="kron")
     assert h.structure == 1 and _lib.Problem.hyper([1, 1, 1], [1, 1, 1], [1, 1, 1], 1.0, "exp").structure == 0
     config_loader.load_settings(_cfg((4, 4, 4)), make_outpath=False)
