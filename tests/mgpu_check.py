@@ -17,12 +17,13 @@ def main():
     worst = 0.0
     cases = [((16, 16, 8), "exp", 5, "fp64"), ((12, 10, 9), "sparse", 0, "fp64"), ((16, 12, 6), "matern32", 7, "fp64"),
              ((16, 16, 16), "exp", 9, "int8x5"), ((12, 11, 32), "matern32", 6, "int8x6"), ((20, 16, 16), "sparse", 0, "int8x5")]
-    structure = "dense"
-    if os.environ.get("GEOBO_B200_MGPU_KRON") == "1":
-        # structure: kron (exp only); 12 x 11 x 16: the two voxel-column shards meet in the middle of an x-z plane
-        structure = "kron"
-        cases = [((12, 11, 16), "exp", 4, "fp64"), ((16, 16, 8), "exp", 0, "fp64"), ((12, 11, 16), "exp", 5, "int8x5")]
-    for shape, kf, nd, prec in cases:
+    cases = [case + ("dense",) for case in cases]
+    if os.environ.get("GEOBO_B200_MGPU_STRUCTURED") == "1":
+        # the opt-in structured projections; 12 x 11 x 16: the two voxel-column shards meet in the middle of an x-z plane
+        cases = [((12, 11, 16), "exp", 4, "fp64", "kron"), ((16, 16, 8), "exp", 0, "fp64", "kron"), ((12, 11, 16), "exp", 5, "int8x5", "kron"),
+                 ((12, 11, 16), "sparse", 4, "fp64", "compact"), ((12, 11, 16), "sparse", 0, "int8x5", "compact"),
+                 ((12, 11, 16), "matern32", 4, "fp64", "fft"), ((16, 16, 8), "sparse", 0, "fp64", "fft"), ((12, 11, 16), "exp", 5, "int8x5", "fft")]
+    for shape, kf, nd, prec, structure in cases:
         cfg = synth.settings(*shape, kernelfunc=kf, precision=prec, structure=structure)
         config_loader.load_settings(cfg, make_outpath=False)
         f = synth.make_inputs(nd=nd, seed=1, ctx=ctx)

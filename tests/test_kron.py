@@ -249,15 +249,15 @@ def test_gpu_kron_fullsize_cfg2_vs_cpu_oracle(prec):
 
 
 @pytest.mark.gpu
-def test_gpu_kron_two_rank_shards_match_oracle():
+def test_gpu_kron_compact_fft_two_rank_shards_match_oracle():
     """Two ranks, voxel-column shards that meet inside an x-z plane: every rank applies the y mode for its own y-rows only and
-    stores its own columns (tests/mgpu_check.py with GEOBO_B200_MGPU_KRON=1)."""
+    stores its own columns; same for the tap-sum and FFT paths (tests/mgpu_check.py with GEOBO_B200_MGPU_STRUCTURED=1)."""
     import sys
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(29950 + os.getpid() % 40), os.path.join(ROOT, "tests", "mgpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, GEOBO_B200_MGPU_KRON="1"))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, GEOBO_B200_MGPU_STRUCTURED="1"))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MGPU_OK world=2" in r.stdout
