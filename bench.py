@@ -284,7 +284,7 @@ def run_ours(args):
                     "mode_product_flops": 12.0 * Ns * (c1 - c0) * (xN + yN + zN) if args.structure == "kron" else None,
                     "dense_flops_replaced": fl["project"],
                     "share_of_step": stage_ms["project"] / ms_per_step, "traffic": None}
-        dtype = ("f64 mode products + " + ("s8 digit slices x%d for A.Pt^T and L^-1.Pt + f64 Cholesky / refinement" % slices if slices else "f64 DMMA"))
+        dtype = ("f64 structured projection (%s) + " % args.structure + ("s8 digit slices x%d for A.Pt^T and L^-1.Pt + f64 Cholesky / refinement" % slices if slices else "f64 DMMA"))
     elif slices:
         # int8 digit-slice kernel: every algorithmic fp64 multiply-add is S(S+1)/2 exact int8 digit products on the
         # tensor cores; the ceiling is the measured dense int8 tcgen05 rate (tools/peaks_i8.cu) divided by that count.

@@ -28,6 +28,7 @@ NOT_YET_RUN_ON_HARDWARE = (
     "test_gpu_kron_",
     "test_gpu_compact_",
     "test_gpu_fft_",
+    "test_gpu_structured_arm_line",
     "test_fullsize_cubing_vs_cpu_oracle",
 )
 

@@ -53,3 +53,15 @@ def test_our_arm_line():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
     assert d["stage_ms"]["project"] > 0 and d["stage_ms"]["chol"] > 0 and d["stage_ms"]["total"] <= d["ms_per_step"] * 1.001
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload,structure", [("cfg1b", "kron"), ("cfg1", "compact"), ("cfg1", "fft")])
+def test_gpu_structured_arm_line(workload, structure):
+    """The opt-in structured projections through bench.py: same contract, the structure named in config, an HBM roofline."""
+    lines = _run(["--workload", workload, "--structure", structure, "--precision", "fp64", "--steps", "2", "--warmup", "3", "--e2e-steps", "1",
+                  "--no-cpu-baseline"])
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert BASE_KEYS <= set(d) and d["config"]["structure"].startswith(structure) and d["value"] > 0 and d["finite"] and d["info"] == 0
+    assert d["roofline"]["bound"] == "hbm" and d["roofline"]["achieved"] > 0 and d["gpu_launches"] > 0
