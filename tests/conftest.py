@@ -9,6 +9,11 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# compile command of the host builds of the device sources (tests/host_harness/*.cpp).  GEOBO_B200_HARNESS_CXXFLAGS adds flags:
+# tests/test_host_harness_asan.py re-runs those tests with -fsanitize=address so that an out-of-bounds index in the per-thread
+# arithmetic of a kernel is caught on the CPU (the harness buffers have exactly the device sizes).
+HARNESS_CXX = ["g++", "-O2", "-ffp-contract=off"] + os.environ.get("GEOBO_B200_HARNESS_CXXFLAGS", "").split() + ["-shared", "-fPIC"]
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden
+from conftest import HARNESS_CXX, ROOT, load_golden
 from oracle import numpy_oracle as o
 
 RTOL = 1e-13
@@ -50,7 +50,7 @@ def host_kernel(tmp_path_factory):
     """csrc/drill.cuh compiled for the host (the same drill_accumulate / drill_finish the CUDA kernel calls)."""
     so = tmp_path_factory.mktemp("drill_host") / "drill_host.so"
     src = os.path.join(ROOT, "tests", "host_harness", "drill_host.cpp")
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", str(so)], check=True)
+    subprocess.run(HARNESS_CXX + [src, "-o", str(so)], check=True)
     lib = ctypes.CDLL(str(so))
     P = ctypes.c_void_p
     lib.drill_host.argtypes = [P, ctypes.c_long, P, P, ctypes.c_long, P, ctypes.c_long, P]

@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import CUBES, ROOT, load_golden, normwise_err
+from conftest import CUBES, HARNESS_CXX, ROOT, load_golden, normwise_err
 from oracle import numpy_oracle as o
 from oracle import stencil as st
 
@@ -84,7 +84,7 @@ def test_oracle_tap_matvec_equals_create_cov_matvec():
 def host(tmp_path_factory):
     so = tmp_path_factory.mktemp("stencil_host") / "stencil_host.so"
     src = os.path.join(ROOT, "tests", "host_harness", "stencil_host.cpp")
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", str(so)], check=True)
+    subprocess.run(HARNESS_CXX + [src, "-o", str(so)], check=True)
     lib = ctypes.CDLL(str(so))
     P, L, D, I = ctypes.c_void_p, ctypes.c_long, ctypes.c_double, ctypes.c_int
     lib.stencil_host_apply.argtypes = [I, P, P, D, P, P, I, P, L, L, L, L, P, L, L, I, P]

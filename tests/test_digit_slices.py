@@ -93,7 +93,8 @@ def test_device_digit_extraction_source_equals_the_restatement(tmp_path):
     if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
         pytest.skip("CUDA headers not found")
     so = tmp_path / "ozaki_host.so"
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I" + cuda_inc,
+    from conftest import HARNESS_CXX
+    subprocess.run(HARNESS_CXX + ["-I" + cuda_inc,
                     os.path.join(root, "tests", "host_harness", "ozaki_host.cpp"), "-o", str(so)], check=True)
     lib = ctypes.CDLL(str(so))
     lib.host_scale_exp.argtypes = [ctypes.c_double]

@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import CUBES, GOLDEN, ROOT, load_golden, normwise_err
+from conftest import CUBES, GOLDEN, HARNESS_CXX, ROOT, load_golden, normwise_err
 from oracle import fftconv as fc
 from oracle import numpy_oracle as o
 
@@ -73,7 +73,7 @@ def test_oracle_fft_matvec_equals_create_cov_matvec(kernel):
 def host(tmp_path_factory):
     so = tmp_path_factory.mktemp("fftconv_host") / "fftconv_host.so"
     src = os.path.join(ROOT, "tests", "host_harness", "fftconv_host.cpp")
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", str(so)], check=True)
+    subprocess.run(HARNESS_CXX + [src, "-o", str(so)], check=True)
     lib = ctypes.CDLL(str(so))
     P, L, D, I = ctypes.c_void_p, ctypes.c_long, ctypes.c_double, ctypes.c_int
     lib.fftconv_host_apply.argtypes = [I, P, P, D, P, P, I, P, L, L, L, L, L, P, L, L, I, P]

@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden
+from conftest import HARNESS_CXX, ROOT, load_golden
 from oracle import numpy_oracle as o
 
 TOL_COV = 1e-13
@@ -26,7 +26,7 @@ KID = {"sparse": 0, "exp": 1, "matern32": 2}
 def host(tmp_path_factory):
     so = tmp_path_factory.mktemp("formulas_host") / "formulas_host.so"
     src = os.path.join(ROOT, "tests", "host_harness", "formulas_host.cpp")
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", str(so)], check=True)
+    subprocess.run(HARNESS_CXX + [src, "-o", str(so)], check=True)
     lib = ctypes.CDLL(str(so))
     for name in ("host_cov_function", "host_create_cov", "host_create_cov_grid", "host_corner_func", "host_a_sens"):
         getattr(lib, name).restype = None

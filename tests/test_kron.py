@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import CUBES, GOLDEN, ROOT, load_golden, normwise_err
+from conftest import CUBES, GOLDEN, HARNESS_CXX, ROOT, load_golden, normwise_err
 from oracle import kron as kr
 from oracle import numpy_oracle as o
 
@@ -77,7 +77,7 @@ def test_oracle_kron_zero_cross_weight_zeroes_the_block():
 def host(tmp_path_factory):
     so = tmp_path_factory.mktemp("kron_host") / "kron_host.so"
     src = os.path.join(ROOT, "tests", "host_harness", "kron_host.cpp")
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", str(so)], check=True)
+    subprocess.run(HARNESS_CXX + [src, "-o", str(so)], check=True)
     lib = ctypes.CDLL(str(so))
     P, L, D, I = ctypes.c_void_p, ctypes.c_long, ctypes.c_double, ctypes.c_int
     lib.kron_host_apply.argtypes = [I, P, P, D, P, P, I, P, L, L, L, L, L, P, L, L, I]
