@@ -7,6 +7,12 @@
 
 #include <vector>
 
+// Thread order inside one phase (between two barriers): 0 = ascending, 1 = descending, 2 = odd ids first.  The result must not
+// depend on it -- a phase in which one thread reads what another one writes would (tests/test_fftconv.py runs all three).
+static int g_order = 0;
+static int tid_at(int i, int n) { return g_order == 0 ? i : g_order == 1 ? n - 1 - i : (i < n / 2 ? 2 * i + 1 : 2 * (i - n / 2)); }
+#define FOR_TID(tid, n) for (int tid##_i = 0, tid = tid_at(0, n); tid##_i < (n); ++tid##_i, tid = tid_at(tid##_i < (n) ? tid##_i : 0, n))
+
 namespace {
 
 // fft_pass_kernel<MODE><<<ceil(nlines / FFT_LPB), FFT_THREADS>>>
@@ -16,16 +22,16 @@ void run_pass(int mode, const FftGeom& g, const FftPass& q, const cplx* in, cons
     cplx* tws = sm.data() + FFT_LPB * q.P;
     const long blocks = (q.nlines + FFT_LPB - 1) / FFT_LPB;
     for (long bx = 0; bx < blocks; ++bx) {
-        for (int tid = 0; tid < FFT_THREADS; ++tid)
+        FOR_TID(tid, FFT_THREADS)
             for (int i = tid; i < q.P / 2; i += FFT_THREADS) tws[i] = tw[i];
         const long line0 = bx * FFT_LPB;
-        for (int tid = 0; tid < FFT_THREADS; ++tid) {
+        FOR_TID(tid, FFT_THREADS) {
             if (mode == 1) fft_load_rows(g, q, A, lda, nrows, line0, tid, FFT_THREADS, sm.data());
             else fft_load(q, in, mul, line0, tid, FFT_THREADS, sm.data());
         }
         for (int s = 1; s <= q.logP; ++s)      // __syncthreads() between the phases
-            for (int tid = 0; tid < FFT_THREADS; ++tid) fft_stage(q, s, tws, tid, FFT_THREADS, sm.data());
-        for (int tid = 0; tid < FFT_THREADS; ++tid) {
+            FOR_TID(tid, FFT_THREADS) fft_stage(q, s, tws, tid, FFT_THREADS, sm.data());
+        FOR_TID(tid, FFT_THREADS) {
             if (mode == 2) fft_store_rows(g, q, rows_out, ldo, nrows, accumulate, line0, tid, FFT_THREADS, sm.data());
             else fft_store(q, out, line0, tid, FFT_THREADS, sm.data());
         }
@@ -35,6 +41,8 @@ void run_pass(int mode, const FftGeom& g, const FftPass& q, const cplx* in, cons
 }  // namespace
 
 extern "C" {
+
+void fftconv_host_set_thread_order(int order) { g_order = order; }
 
 // out[s][r * r_stride_out + (j - c0)] (+)= sum_i A[s][i] * K_(blk0 + r)[i][j],  rows s < nrows, r = 0..2, j in [c0, c1)
 // B: complex row pairs per chunk; padded_out: (Py, Px, Pz)

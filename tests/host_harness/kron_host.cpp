@@ -7,7 +7,15 @@
 
 #include <vector>
 
+// Thread order inside one phase (between two barriers): 0 = ascending, 1 = descending, 2 = odd ids first.  The result must not
+// depend on it -- a phase in which one thread reads what another one writes would (tests/test_kron.py runs all three).
+static int g_order = 0;
+static int tid_at(int i, int n) { return g_order == 0 ? i : g_order == 1 ? n - 1 - i : (i < n / 2 ? 2 * i + 1 : 2 * (i - n / 2)); }
+#define FOR_TID(tid, n) for (int tid##_i = 0, tid = tid_at(0, n); tid##_i < (n); ++tid##_i, tid = tid_at(tid##_i < (n) ? tid##_i : 0, n))
+
 extern "C" {
+
+void kron_host_set_thread_order(int order) { g_order = order; }
 
 // out[s][r * r_stride_out + (j - c0)] (+)= sum_i A[s][i] * K_(blk0 + r)[i][j],  rows s < nrows, r = 0..2, j in [c0, c1)
 void kron_host_apply(int kernel_id, const double* l, const double* w, double amp, const long* ncube, const double* vox, int blk0,
@@ -32,7 +40,7 @@ void kron_host_apply(int kernel_id, const double* l, const double* w, double amp
     for (int b = 0; b < 9; ++b)
         for (int axis = 0; axis < 3; ++axis)
             for (int bx = 0; bx < (g.FL + 127) / 128; ++bx)
-                for (int tid = 0; tid < 128; ++tid) {
+                FOR_TID(tid, 128) {
                     const int i = bx * 128 + tid;
                     if (i < g.FL) kf[((long)b * 3 + axis) * g.FL + i] = kron_factor(tab.data() + (long)b * ext + C0, g, axis, i);
                 }
@@ -51,10 +59,10 @@ void kron_host_apply(int kernel_id, const double* l, const double* w, double amp
             for (int by = 0; by < jgroups; ++by)
                 for (int bx = 0; bx < qtiles; ++bx) {
                     double* sf = smem.data();
-                    for (int tid = 0; tid < KRON_YTHREADS; ++tid)
+                    FOR_TID(tid, KRON_YTHREADS)
                         for (int i = tid; i < 3 * g.FL; i += KRON_YTHREADS) sf[i] = kf[((long)(blk0 + i / g.FL) * 3 + 0) * g.FL + i % g.FL];
                     // __syncthreads()
-                    for (int tid = 0; tid < KRON_YTHREADS; ++tid)
+                    FOR_TID(tid, KRON_YTHREADS)
                         kron_y_thread(g, A + s0 * lda + bz * lda, sf, bx, by, tid, T.data() + bz * g.nyl * g.XZ, r_stride);
                 }
         // kron_zx_kernel<<<(nyl, n, 3), KRON_ZXTHREADS>>>
@@ -66,12 +74,12 @@ void kron_host_apply(int kernel_id, const double* l, const double* w, double amp
                     double* fx = ptmp + (long)g.xN * g.zs;
                     double* fz = fx + g.FL;
                     const double* kfb = kf.data() + (long)(blk0 + r) * 3 * g.FL;
-                    for (int tid = 0; tid < KRON_ZXTHREADS; ++tid)
+                    FOR_TID(tid, KRON_ZXTHREADS)
                         kron_zx_load(g, T.data() + r * r_stride + (sl * g.nyl + jl) * g.XZ, kfb + g.FL, kfb + 2 * g.FL, tid, KRON_ZXTHREADS, pin, fx, fz);
                     // __syncthreads()
-                    for (int tid = 0; tid < KRON_ZXTHREADS; ++tid) kron_z_phase(g, pin, fz, tid, KRON_ZXTHREADS, ptmp);
+                    FOR_TID(tid, KRON_ZXTHREADS) kron_z_phase(g, pin, fz, tid, KRON_ZXTHREADS, ptmp);
                     // __syncthreads()
-                    for (int tid = 0; tid < KRON_ZXTHREADS; ++tid)
+                    FOR_TID(tid, KRON_ZXTHREADS)
                         kron_x_phase(g, ptmp, fx, g.jy0 + jl, tid, KRON_ZXTHREADS, out + (s0 + sl) * ldo + r * r_stride_out, accumulate);
                 }
     }

@@ -78,6 +78,7 @@ def host(tmp_path_factory):
     P, L, D, I = ctypes.c_void_p, ctypes.c_long, ctypes.c_double, ctypes.c_int
     lib.fftconv_host_apply.argtypes = [I, P, P, D, P, P, I, P, L, L, L, L, L, P, L, L, I, P]
     lib.fftconv_host_apply.restype = None
+    lib.fftconv_host_set_thread_order.argtypes = [I]
 
     def apply(c, params, w, amp, blk0, A, c0, c1, B, out, ldo, r_stride_out, accumulate):
         p = lambda a: a.ctypes.data_as(P)                                            # noqa: E731
@@ -91,6 +92,7 @@ def host(tmp_path_factory):
         lib.fftconv_host_apply(KID[c.kernelfunc], p(l), p(ww), amp, p(ncube), p(vox), blk0, p(A), A.shape[1], A.shape[0], c0, c1, B, p(out), ldo,
                                r_stride_out, accumulate, p(pad))
         return tuple(int(v) for v in pad)
+    apply.set_thread_order = lib.fftconv_host_set_thread_order
     return apply
 
 
@@ -119,6 +121,20 @@ def test_host_compiled_kernels_vs_dense_oracle(host, shape, kernel, shard, nrows
     got = Pt[:, :, :c1 - c0]
     assert np.isfinite(got).all() and np.isnan(Pt[:, :, c1 - c0:]).all()             # exactly the shard's columns were written
     assert np.abs(got - dense[:, :, c0:c1]).max() <= TOL * np.abs(dense).max()
+
+
+def test_host_compiled_kernels_do_not_depend_on_the_thread_order_inside_a_phase(host):
+    """Between two barriers (load | every butterfly stage | store) the harness may run the threads of a block in any order: a
+    stage in which two threads touch the same element would give a different result."""
+    c, N, A, params, w, amp = _case((5, 6, 7), "matern32", 9, nrows=3)
+    try:
+        res = []
+        for order in (0, 1, 2):
+            host.set_thread_order(order)
+            res.append(_host_projection(host, c, params, w, amp, A, 32, 176, 1)[0])
+    finally:
+        host.set_thread_order(0)
+    assert np.array_equal(res[0], res[1], equal_nan=True) and np.array_equal(res[0], res[2], equal_nan=True)
 
 
 def test_host_compiled_matvec_accumulates_over_data_blocks(host):

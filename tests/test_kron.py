@@ -82,6 +82,7 @@ def host(tmp_path_factory):
     P, L, D, I = ctypes.c_void_p, ctypes.c_long, ctypes.c_double, ctypes.c_int
     lib.kron_host_apply.argtypes = [I, P, P, D, P, P, I, P, L, L, L, L, L, P, L, L, I]
     lib.kron_host_apply.restype = None
+    lib.kron_host_set_thread_order.argtypes = [I]
 
     def apply(c, params, w, amp, blk0, A, c0, c1, chunk_rows, out, ldo, r_stride_out, accumulate, kernel="exp"):
         p = lambda a: a.ctypes.data_as(P)                                            # noqa: E731
@@ -93,6 +94,7 @@ def host(tmp_path_factory):
         assert out.flags.c_contiguous and out.dtype == np.float64
         lib.kron_host_apply(KID[kernel], p(l), p(ww), amp, p(ncube), p(vox), blk0, p(A), A.shape[1], A.shape[0], c0, c1, chunk_rows, p(out),
                             ldo, r_stride_out, accumulate)
+    apply.set_thread_order = lib.kron_host_set_thread_order
     return apply
 
 
@@ -122,6 +124,20 @@ def test_host_compiled_kernels_vs_dense_oracle(host, shape, shard, chunk):
     assert np.isfinite(got).all()                                                    # every column of the shard was written
     assert np.isnan(Pt[:, :, c1 - c0:]).all()                                        # and nothing outside it
     assert np.abs(got - dense[:, :, c0:c1]).max() <= 1e-13 * np.abs(dense).max()
+
+
+def test_host_compiled_kernels_do_not_depend_on_the_thread_order_inside_a_phase(host):
+    """Between two barriers the harness may run the threads of a block in any order (ascending, descending, odd ids first): a
+    phase in which one thread reads what another one writes would give a different result."""
+    c, N, A, params, w, amp = _case((5, 11, 6), 9, nrows=3)
+    try:
+        res = []
+        for order in (0, 1, 2):
+            host.set_thread_order(order)
+            res.append(_host_projection(host, c, params, w, amp, A, 48, 272, 2))
+    finally:
+        host.set_thread_order(0)
+    assert np.array_equal(res[0], res[1], equal_nan=True) and np.array_equal(res[0], res[2], equal_nan=True)
 
 
 def test_host_compiled_matvec_accumulates_over_data_blocks(host):
