@@ -233,3 +233,38 @@ def test_gpu_fft_fullsize_cfg3_vs_cpu_oracle(prec):
         assert np.abs(got[::stride] - sub).max() / ref_max < 1e-5, n
         assert abs(float(got.sum()) - float(g["sum_" + n])) / (N * ref_max) < 1e-5, n
     assert abs(inv.logl - float(g["logl"])) < (1e-6 if prec == "fp64" else 1e-4) * abs(float(g["logl"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel,structure", [("exp", "kron"), ("sparse", "compact"), ("matern32", "fft"), ("exp", "fft")])
+def test_gpu_fft_and_friends_calc_logl_vs_oracle(kernel, structure):
+    """Inversion.calc_logl (inversion.py:125-152; the objective optimize_gp evaluates hundreds of times) through the structured
+    projections against the oracle's objective."""
+    from geobo_b200 import _lib, config_loader, inversion
+    from test_gpu_parity import synthetic_inputs
+    cfg = _cfg((6, 5, 4), kernel, structure=structure)
+    c = o.make_config(cfg)
+    f = synthetic_inputs(c, 4)
+    config_loader.load_settings(cfg, make_outpath=False)
+    inv = inversion.Inversion()
+    inv.create_cubegeometry()
+    if kernel == "matern32":
+        inv.gp_length = inv.gp_length * np.array([1.0, 1.01, 1.02])
+    try:
+        inv.cubing(f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"])
+        E, vp = o.cube_geometry(c)
+        A = [o.a_sens(c, c.magneticField * 0, f["sensor_locations"], E, "grav"), o.a_sens(c, c.magneticField, f["sensor_locations"], E, "magn")]
+        didx = o.drill_indices(f["drilldata0"])
+        for params in ([1.0, 2.0, 1.0, 0.2, 0.2], [1.7, 3.1, 0.6, 0.5, 0.9]):
+            with np.errstate(all="ignore"):
+                ref = o.calc_logl(c, A, didx, inv.Fs3, params)
+            got = inv.calc_logl(params)
+            if np.isfinite(ref):
+                assert abs(got - ref) < 1e-7 * abs(ref), (params, got, ref)
+            else:
+                assert got == np.inf                                                  # matern32 with one common scale is singular
+    finally:
+        if inv._problem is not None:
+            inv._problem.close()
+            inv._problem = None
+        _lib.default_context().release_cache()
