@@ -262,7 +262,7 @@ def test_gpu_fft_and_friends_calc_logl_vs_oracle(kernel, structure):
             if np.isfinite(ref):
                 assert abs(got - ref) < 1e-7 * abs(ref), (params, got, ref)
             else:
-                assert got == np.inf                                                  # matern32 with one common scale is singular
+                assert not np.isfinite(got)                                           # matern32 with one common scale is singular
     finally:
         if inv._problem is not None:
             inv._problem.close()
