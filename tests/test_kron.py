@@ -194,7 +194,7 @@ def _gpu_cubing(cfg, f, gl=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,nd,prec", [((7, 5, 3), 3, "fp64"), ((5, 11, 6), 0, "fp64"), ((20, 3, 16), 4, "fp64"),
+@pytest.mark.parametrize("shape,nd,prec", [((7, 5, 3), 3, "fp64"), ((5, 11, 6), 0, "fp64"), ((20, 4, 16), 4, "fp64"),
                                            ((5, 4, 16), 3, "int8x5"), ((11, 4, 48), 0, "int8x6")])
 def test_gpu_kron_cubing_vs_oracle(shape, nd, prec):
     from test_gpu_parity import synthetic_inputs
