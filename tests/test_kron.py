@@ -223,7 +223,7 @@ def test_gpu_kron_matches_dense_device_path_and_scratch_chunks(monkeypatch):
     _, kron_small, _ = _gpu_cubing(dict(cfg, structure="kron"), f)
     for n, a, b, b2 in zip(CUBES, dense, kron, kron_small):
         assert normwise_err(b, a) < 1e-9, n
-        assert np.array_equal(b, b2), n
+        assert normwise_err(b2, b) < 1e-12, n      # same arithmetic per row whatever the chunking
 
 
 @pytest.mark.gpu
