@@ -96,10 +96,13 @@ class Inversion:
         'compact' : for ``kernelfunc: 'sparse'`` only -- the compact-support kernels (``kernels.py:101-138``) vanish beyond
         their length scale, so the products with ``kcov`` run as a tap sum over the offsets inside the support;
         'fft'   : any kernel -- every block of ``create_cov`` is block-Toeplitz on the voxel grid, so the products with
-        ``kcov`` run as zero-padded 3-D FFT convolutions with the block's values on the offset lattice (fp64)."""
+        ``kcov`` run as zero-padded 3-D FFT convolutions with the block's values on the offset lattice (fp64);
+        'auto'  : 'kron' for 'exp', 'compact' for 'sparse', 'fft' otherwise."""
         st = str(getattr(_cfg, "structure", "dense")).lower()
+        if st == "auto":        # the cheapest structured form the kernel family admits
+            return {"exp": "kron", "sparse": "compact"}.get(_cfg.kernelfunc, "fft")
         if st not in _lib.STRUCTURE_IDS:
-            raise ValueError("settings key 'structure' must be 'dense', 'kron', 'compact' or 'fft', got %r" % st)
+            raise ValueError("settings key 'structure' must be 'dense', 'kron', 'compact', 'fft' or 'auto', got %r" % st)
         return st
 
     def _hyper(self, gp_length=None, coeffm=None, gp_amp=None):

@@ -172,6 +172,9 @@ def test_structure_key_is_validated():
     assert h.structure == 1 and _lib.Problem.hyper([1, 1, 1], [1, 1, 1], [1, 1, 1], 1.0, "exp").structure == 0
     config_loader.load_settings(_cfg((4, 4, 4)), make_outpath=False)
     assert inversion.Inversion()._structure() == "dense"                             # reference YAMLs have no such key
+    for kf, want in (("exp", "kron"), ("sparse", "compact"), ("matern32", "fft")):
+        config_loader.load_settings(dict(_cfg((4, 4, 4), structure="auto"), kernelfunc=kf), make_outpath=False)
+        assert inversion.Inversion()._structure() == want
 
 
 # ------------------------------------------------------------------------------------------------ GPU
