@@ -193,7 +193,7 @@ def run(name, structure, workers, rows_per_job):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("workload", choices=["cfg2", "cfg3"])
+    ap.add_argument("workload", choices=["cfg2", "cfg3", "cfg3e"])
     ap.add_argument("structure", choices=["kron", "fft"])
     ap.add_argument("--workers", type=int, default=max(1, (os.cpu_count() or 2) - 1))
     ap.add_argument("--rows-per-job", type=int, default=16)

@@ -3,6 +3,7 @@
 
     python tests/golden/make_fullsize_golden.py cfg2 [--workers 6]     # 32x32x32, exp, nd = 0        (minutes)
     python tests/golden/make_fullsize_golden.py cfg3 [--workers 6]     # 64x64x32, matern32, nd = 50  (about 1.5 h on 6 cores)
+    python tests/golden/make_fullsize_golden.py cfg3e [--workers 7]    # 64x64x32, exp, nd = 0        (about 1 h on 7 cores)
 
 Build-container job (CPU only, nothing here needs the reference tree or a GPU).  It runs the oracle's lean
 restatement of ``Inversion.cubing`` (``oracle/numpy_oracle.py``: ``a_sens``, ``pt_panel``, the arithmetic of
@@ -34,6 +35,8 @@ WORKLOADS = {   # bench.py WORKLOADS
     "check": dict(shape=(8, 6, 16), kernel="matern32", nd=5, gl_mult=(1.0, 1.01, 1.02), stride=1, panel=128),
     "cfg2": dict(shape=(32, 32, 32), kernel="exp", nd=0, gl_mult=(1.0, 1.0, 1.0), stride=3, panel=2048),
     "cfg3": dict(shape=(64, 64, 32), kernel="matern32", nd=50, gl_mult=(1.0, 1.01, 1.02), stride=5, panel=2048),
+    # the north star's target cube: 64x64x32, two properties (no drill data), squared-exponential kernel (bench workload cfg3e)
+    "cfg3e": dict(shape=(64, 64, 32), kernel="exp", nd=0, gl_mult=(1.0, 1.0, 1.0), stride=5, panel=2048),
 }
 
 G = {}   # inherited by the forked workers

@@ -241,12 +241,13 @@ def test_gpu_kron_refuses_non_separable_kernels(kf):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("prec", ["fp64", "int8x5"])
-def test_gpu_kron_fullsize_cfg2_vs_cpu_oracle(prec):
-    """BASELINE config 2 (32x32x32, exp) through structure kron against the oracle's full-size result (1e-5, north star)."""
-    if not os.path.exists(os.path.join(GOLDEN, "fullsize_cfg2.npz")):
-        pytest.skip("fixture fullsize_cfg2.npz not generated")
-    g = load_golden("fullsize_cfg2.npz")
+@pytest.mark.parametrize("name,prec", [("cfg2", "fp64"), ("cfg2", "int8x5"), ("cfg3e", "int8x5")])
+def test_gpu_kron_fullsize_vs_cpu_oracle(name, prec):
+    """BASELINE config 2 (32x32x32, exp) and the north star's 64x64x32 two-property cube (exp) through structure kron against the
+    dense oracle's full-size results (1e-5, north star)."""
+    if not os.path.exists(os.path.join(GOLDEN, "fullsize_%s.npz" % name)):
+        pytest.skip("fixture fullsize_%s.npz not generated" % name)
+    g = load_golden("fullsize_%s.npz" % name)
     cfg = dict(json.loads(str(g["cfg"])), precision=prec, structure="kron")
     c = o.make_config(cfg)
     N = c.xNcube * c.yNcube * c.zNcube

@@ -1,7 +1,8 @@
 """Parity at BASELINE's full sizes against results of the CPU oracle computed in full.
 
-``tests/golden/fullsize_cfg2.npz`` (32x32x32, exp, nd = 0, M = 2048) and ``fullsize_cfg3.npz`` (64x64x32, matern32 with
-scales L.[1, 1.01, 1.02], nd = 50, M = 8242) hold the inputs and every ``stride``-th voxel of the six result cubes of one
+``tests/golden/fullsize_cfg2.npz`` (32x32x32, exp, nd = 0, M = 2048), ``fullsize_cfg3.npz`` (64x64x32, matern32 with
+scales L.[1, 1.01, 1.02], nd = 50, M = 8242) and ``fullsize_cfg3e.npz`` (64x64x32, exp, nd = 0, M = 8192: the north star's
+"64x64x32 two-property cube") hold the inputs and every ``stride``-th voxel of the six result cubes of one
 complete oracle inversion (``tests/golden/make_fullsize_golden.py``, run once in the build container: 107 s / about
 1.5 h on 6-7 cores), plus max|cube| and sum(cube) over the full cubes.  The device path gets exactly the stored inputs
 through ``Inversion.cubing`` and must reproduce them within the tolerance the north star states: 1e-5 relative on
@@ -36,7 +37,7 @@ def _inputs(g):
     return cfg, d0
 
 
-@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg3e"])
 def test_fullsize_fixture_is_what_the_generator_describes(name):
     """CPU: provenance of the fixture -- the stored surveys are the oracle's forward simulation of the bench's truth
     cube (checked on a few sensors), the drill values sit on the drilled voxels, the sub-sampled cubes have the
@@ -74,7 +75,7 @@ def test_fullsize_fixture_is_what_the_generator_describes(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,prec", [("cfg2", "fp64"), ("cfg2", "int8x5"), ("cfg3", "int8x5"), ("cfg3", "fp64")])
+@pytest.mark.parametrize("name,prec", [("cfg2", "fp64"), ("cfg2", "int8x5"), ("cfg3", "int8x5"), ("cfg3e", "int8x5"), ("cfg3", "fp64")])
 def test_fullsize_cubing_vs_cpu_oracle(name, prec):
     if not _have(name):
         pytest.skip("fixture fullsize_%s.npz not generated" % name)
