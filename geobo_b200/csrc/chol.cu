@@ -237,6 +237,30 @@ static int chol_outer_panels() {
     return outer;
 }
 
+// GEOBO_B200_CHOL_LOOKAHEAD=1 (default 0): the trailing update of an outer block is split into the columns of the next outer
+// block (main stream) and the rest (side stream), so that the sequential potrf128 / panel-solve chain of the next block runs
+// concurrently with the bulk of the update instead of after it.  Same arithmetic per element, same order of the updates of
+// every element (all (b) parts are stream ordered, (a) of block j waits for (b) of block j - 1): results are bit-identical.
+struct CholLookahead {
+    bool on = false, ready = false, b_pending = false;
+    cudaStream_t side = nullptr;
+    cudaEvent_t panels = nullptr, b_done = nullptr;
+};
+static CholLookahead la;
+
+static cudaError_t chol_lookahead_setup() {
+    la.on = false;
+    la.b_pending = false;
+    if (const char* ev = getenv("GEOBO_B200_CHOL_LOOKAHEAD")) la.on = atoi(ev) != 0;
+    if (!la.on || la.ready) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&la.side, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&la.panels, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&la.b_done, cudaEventDisableTiming)) != cudaSuccess) return e;
+    la.ready = true;
+    return cudaSuccess;
+}
+
 cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, cudaStream_t s) {
     static bool attr_set = false;
     const int smem = (NB * PLD + 64 * 64 + NB) * (int)sizeof(double);
@@ -248,6 +272,7 @@ cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork&
     }
     const int nblk = Mp / NB;
     const int outer = chol_outer_panels();
+    if ((e = chol_lookahead_setup()) != cudaSuccess) return e;
     for (int ob = 0; ob < nblk; ob += outer) {
         const int o0 = ob * NB, oe = (ob + outer < nblk ? ob + outer : nblk), o1 = oe * NB;
         for (int kb = ob; kb < oe; ++kb) {
@@ -282,9 +307,35 @@ cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork&
         double* trail = Bm + (long)o1 * ldb + o1;
         gemm::TaskBatch b2;
         b2.n = 1;
-        b2.t[0] = make_task(lp, ldb, lp, ldb, trail, ldb, trail, ldb, rest, rest, o1 - o0, -1.0, 1.0, 1);
-        e = gemm::launch(b2, gemm::B_T, s);
-        if (e != cudaSuccess) return e;
+        if (!la.on) {
+            b2.t[0] = make_task(lp, ldb, lp, ldb, trail, ldb, trail, ldb, rest, rest, o1 - o0, -1.0, 1.0, 1);
+            e = gemm::launch(b2, gemm::B_T, s);
+            if (e != cudaSuccess) return e;
+            continue;
+        }
+        // look-ahead: (a) the columns of the NEXT outer block on the main stream, so that its panels can start at once;
+        // (b) everything to the right of them on the side stream, concurrently with those panels.  Both (a) of this block and
+        // (b) of the previous one update the next block's columns, and (b) needs this block's finished panels:
+        //   main: wait (b) of the previous block -> (a);   side: wait the panels of this block -> (b)   [(b)s are stream ordered]
+        const int wdt = (outer * NB < rest) ? outer * NB : rest;
+        if ((e = cudaEventRecord(la.panels, s)) != cudaSuccess) return e;
+        if (la.b_pending && (e = cudaStreamWaitEvent(s, la.b_done, 0)) != cudaSuccess) return e;
+        b2.t[0] = make_task(lp, ldb, lp, ldb, trail, ldb, trail, ldb, rest, wdt, o1 - o0, -1.0, 1.0, 1);
+        if ((e = gemm::launch(b2, gemm::B_T, s)) != cudaSuccess) return e;
+        la.b_pending = false;
+        if (rest > wdt) {
+            if ((e = cudaStreamWaitEvent(la.side, la.panels, 0)) != cudaSuccess) return e;
+            double* lp2 = lp + (long)wdt * ldb;
+            double* trail2 = trail + (long)wdt * ldb + wdt;
+            b2.t[0] = make_task(lp2, ldb, lp2, ldb, trail2, ldb, trail2, ldb, rest - wdt, rest - wdt, o1 - o0, -1.0, 1.0, 1);
+            if ((e = gemm::launch(b2, gemm::B_T, la.side)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(la.b_done, la.side)) != cudaSuccess) return e;
+            la.b_pending = true;
+        }
+    }
+    if (la.on && la.b_pending) {
+        if ((e = cudaStreamWaitEvent(s, la.b_done, 0)) != cudaSuccess) return e;
+        la.b_pending = false;
     }
     return cudaSuccess;
 }

@@ -223,6 +223,24 @@ def test_two_level_cholesky_flag_vs_oracle(ctx, monkeypatch):
     assert abs(inv.logl - ex["logl"]) < 1e-7 * abs(ex["logl"])
 
 
+@pytest.mark.parametrize("outer", ["1", "4"])
+def test_cholesky_lookahead_flag_vs_oracle(ctx, monkeypatch, outer):
+    """GEOBO_B200_CHOL_LOOKAHEAD=1: the trailing update is split into the next block's columns (main stream) and the rest (side
+    stream, concurrent with the next panels).  Every element sees the same updates in the same order, so the cubes must equal
+    those of the plain factorisation (to rounding at most) -- and the oracle's within the parity tolerance."""
+    c = configure(base_cfg(), xNcube=24, yNcube=24, zNcube=4, kernelfunc="exp")
+    f = synthetic_inputs(c, 3)
+    ref, ex = o.cubing_lean(c, f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"])
+    monkeypatch.setenv("GEOBO_B200_CHOL_OUTER", outer)
+    _, plain = run_cubing(f)
+    monkeypatch.setenv("GEOBO_B200_CHOL_LOOKAHEAD", "1")
+    inv, out = run_cubing(f)
+    for n, a, b, r in zip(CUBES, out, plain, ref):
+        assert normwise_err(a, r) < TOL_CUBE, n
+        assert normwise_err(a, b) < 1e-12, n
+    assert abs(inv.logl - ex["logl"]) < 1e-7 * abs(ex["logl"])
+
+
 def test_not_positive_definite_exits_like_reference(ctx, capsys):
     """matern32 with equal scales: 0/0 in the cross term -> Cholesky fails -> two prints + sys.exit(1) (inversion.py:99-104)."""
     c = configure(base_cfg(), xNcube=6, yNcube=5, zNcube=4, kernelfunc="matern32")
