@@ -281,3 +281,35 @@ def test_gpu_kron_compact_fft_two_rank_shards_match_oracle():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, GEOBO_B200_MGPU_STRUCTURED="1"))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MGPU_OK world=2" in r.stdout
+
+
+# ------------------------------------------------------------------------------------------------ CPU: outputs of the unmodified reference
+@pytest.mark.parametrize("name,structure", [("exp_nd7", "kron"), ("exp_nd0", "kron"), ("exp_nd7", "fft"), ("matern32_nd7", "fft"), ("sparse_nd7", "compact")])
+def test_structured_oracle_reproduces_the_live_reference_fixtures(monkeypatch, name, structure):
+    """tests/golden/cubing_*.npz hold Inversion.cubing outputs of the UNMODIFIED reference (make_golden.py).  The oracle's lean
+    pipeline with Pt from the structured restatements reproduces them to the same 1e-7 as with the dense panels."""
+    from oracle import fftconv as fc
+    from oracle import stencil as st
+    f = load_golden("cubing_%s.npz" % name)
+    c = o.make_config(json.loads(str(f["cfg"])))
+    cache = {}
+    dense_panel = o.pt_panel
+
+    def structured_panel(c_, params, w, amp, A_list, didx, pts, cols, **kw):
+        if cache.get("building"):                  # the drill rows inside the structured restatements stay dense gathers
+            return dense_panel(c_, params, w, amp, A_list, didx, pts, cols, **kw)
+        if "pt" not in cache:
+            cache["building"] = True
+            cache["pt"] = {"kron": lambda: kr.pt_kron(c_, params, w, amp, A_list, didx),
+                           "compact": lambda: st.pt_compact(c_, params, w, amp, A_list, didx),
+                           "fft": lambda: fc.pt_fft(c_, params, w, amp, c_.kernelfunc, A_list, didx)}[structure]()
+            cache["building"] = False
+        return cache["pt"][:, :, cols]
+
+    monkeypatch.setattr(o, "pt_panel", structured_panel)
+    with np.errstate(all="ignore"):
+        cubes, ex = o.cubing_lean(c, f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"], gp_length=np.array(f["gl_before"], dtype=float))
+    assert "pt" in cache
+    for n, a in zip(CUBES, cubes):
+        assert normwise_err(a, f[n]) < 1e-7, n
+    assert abs(ex["logl"] - float(f["logl"])) < 1e-7 * abs(float(f["logl"]))
