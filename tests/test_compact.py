@@ -241,3 +241,47 @@ def test_structured_oracle_reproduces_the_committed_vtk_goldens(monkeypatch, whi
     for n, a in zip(CUBES, cubes):
         assert normwise_err(a, f["gold_" + n]) < 2e-7, n          # the VTK files come from an older BLAS stack (<= 4e-8)
     assert abs(ex["logl"] - float(f["logl"])) < 1e-6
+
+
+def _pipeline_with_projection(monkeypatch, c, f, project, gp_length=None):
+    """The oracle's lean pipeline with the two survey blocks of Pt supplied by ``project(params, w, amp, A_list)`` -> (2 Ns, 3, N);
+    the drill rows stay the oracle's dense gathers."""
+    cache = {}
+    dense_panel = o.pt_panel
+
+    def panel(c_, params, w, amp, A_list, didx, pts, cols, **kw):
+        if "pt" not in cache:
+            Ns = A_list[0].shape[0]
+            N = A_list[0].shape[1]
+            full = np.zeros((2 * Ns + didx.size, 3, N))
+            full[:2 * Ns] = project(params, w, amp, A_list)
+            if didx.size:
+                zero_rows = [np.zeros((1, N)), np.zeros((1, N))]           # only the drill rows of the dense panel are wanted
+                full[2 * Ns:] = dense_panel(c_, params, w, amp, zero_rows, didx, pts, np.arange(N))[2:]
+            cache["pt"] = full
+        return cache["pt"][:, :, cols]
+
+    monkeypatch.setattr(o, "pt_panel", panel)
+    with np.errstate(all="ignore"):
+        kw = {} if gp_length is None else {"gp_length": np.array(gp_length, dtype=float)}
+        cubes, ex = o.cubing_lean(c, f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"], **kw)
+    assert "pt" in cache
+    return cubes, ex
+
+
+def test_host_compiled_kernel_reproduces_the_committed_vtk_goldens(host, monkeypatch):
+    """Example 1 of the reference (25 x 16 x 16, sparse kernel, M = 1056) with Pt computed by the DEVICE SOURCE of the tap-sum kernel
+    (csrc/stencil.cuh compiled for the host, tables from csrc/formulas.cuh): the committed VTK cubes are reproduced to 2e-7."""
+    f = load_golden("example1.npz")
+    c = o.make_config(json.loads(str(f["cfg"])))
+
+    def project(params, w, amp, A_list):
+        N = A_list[0].shape[1]
+        Pt, win = _host_projection(host, c, params, w, amp, A_list, 0, N)
+        assert win == (2, 2, 4)
+        return Pt[:, :, :N]
+
+    cubes, ex = _pipeline_with_projection(monkeypatch, c, f, project)
+    for n, a in zip(CUBES, cubes):
+        assert normwise_err(a, f["gold_" + n]) < 2e-7, n
+    assert abs(ex["logl"] - float(f["logl"])) < 1e-6

@@ -268,3 +268,21 @@ def test_gpu_fft_and_friends_calc_logl_vs_oracle(kernel, structure):
             inv._problem.close()
             inv._problem = None
         _lib.default_context().release_cache()
+
+
+@pytest.mark.parametrize("name", ["matern32_nd7", "sparse_nd7", "exp_nd7"])
+def test_host_compiled_kernels_reproduce_the_live_reference_fixture(host, monkeypatch, name):
+    """Outputs of the unmodified reference (all three kernels, tiny cube) with Pt computed by the DEVICE SOURCE of the FFT passes
+    (csrc/fftconv.cuh compiled for the host, tables from csrc/formulas.cuh) inside the oracle's lean pipeline."""
+    from test_compact import _pipeline_with_projection
+    f = load_golden("cubing_%s.npz" % name)
+    c = o.make_config(json.loads(str(f["cfg"])))
+
+    def project(params, w, amp, A_list):
+        N = A_list[0].shape[1]
+        return _host_projection(host, c, params, w, amp, A_list, 0, N, 3)[0][:, :, :N]
+
+    cubes, ex = _pipeline_with_projection(monkeypatch, c, f, project, gp_length=f["gl_before"])
+    for n, a in zip(CUBES, cubes):
+        assert normwise_err(a, f[n]) < 1e-7, n
+    assert abs(ex["logl"] - float(f["logl"])) < 1e-7 * abs(float(f["logl"]))

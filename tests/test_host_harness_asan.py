@@ -20,7 +20,8 @@ def test_host_harness_tests_pass_under_address_sanitizer():
         pytest.skip("libasan.so not available")
     env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1",
                GEOBO_B200_HARNESS_CXXFLAGS="-fsanitize=address -fno-omit-frame-pointer -g")
-    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "not gpu", "-p", "no:cacheprovider"] + HOST_TESTS, cwd=ROOT, env=env,
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "not gpu", "-p", "no:cacheprovider",
+                        "-k", "not test_oracle and not test_structured_oracle"] + HOST_TESTS,      # NumPy-only tests have no harness to check cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=1200)
     tail = r.stdout[-3000:] + r.stderr[-3000:]
     assert r.returncode == 0 and "AddressSanitizer" not in tail, tail
