@@ -4,6 +4,7 @@
     python tests/golden/check_fullsize_structured.py cfg2 kron  [--workers 7]     # 32x32x32, exp       (about a minute)
     python tests/golden/check_fullsize_structured.py cfg2 fft
     python tests/golden/check_fullsize_structured.py cfg3 fft                     # 64x64x32, matern32  (tens of minutes)
+    python tests/golden/check_fullsize_structured.py cfg2 kron-host               # Pt from csrc/kron.cuh compiled for the host
 
 Build-container job (CPU only).  ``fullsize_<cfg>.npz`` holds the result of the oracle's DENSE lean path
 (``make_fullsize_golden.py``: every covariance entry evaluated, dgemm projection).  This script recomputes the same inversion
@@ -41,8 +42,11 @@ def _rows_job(job):
     with threadpool_limits(1):
         pt = np.memmap(G["pt_path"], dtype=np.float64, mode="r+", shape=(npanel, M, 3, panel))
         X = A[cb][s0:s1]
+        host_out = _host_rows(cb, X) if G["structure"].endswith("-host") else None
         for r in range(3):
-            if G["structure"] == "kron":
+            if host_out is not None:
+                out = host_out[:, r, :]
+            elif G["structure"] == "kron":
                 from oracle import kron as kr
                 out = kr.apply_block(c, params, w, amp, cb, r, X)
             else:
@@ -53,6 +57,34 @@ def _rows_job(job):
         pt.flush()
         del pt
     return time.perf_counter() - t0
+
+
+def _host_rows(cb, X):
+    """Rows of Pt from the DEVICE SOURCE compiled for the host (tests/host_harness/kron_host.cpp / fftconv_host.cpp: the per-thread
+    code of csrc/kron.cuh / csrc/fftconv.cuh driven with the launch geometry of the kernels) -> (rows, 3, N)."""
+    import ctypes
+    c, params, w, amp, N = (G[k] for k in ("c", "params", "w", "amp", "N"))
+    lib = ctypes.CDLL(G["host_so"])
+    P, L, D, I = ctypes.c_void_p, ctypes.c_long, ctypes.c_double, ctypes.c_int
+    p = lambda a: a.ctypes.data_as(P)                                            # noqa: E731
+    l = np.ascontiguousarray(params, dtype=float)
+    ww = np.ascontiguousarray(w, dtype=float)
+    ncube = np.array([c.xNcube, c.yNcube, c.zNcube], dtype=np.int64)
+    vox = np.array([c.xvoxsize, c.yvoxsize, c.zvoxsize], dtype=float)
+    X = np.ascontiguousarray(X, dtype=float)
+    out = np.full((X.shape[0], 3 * N), np.nan)
+    kid = {"sparse": 0, "exp": 1, "matern32": 2}[c.kernelfunc]
+    if G["structure"] == "kron-host":
+        lib.kron_host_apply.argtypes = [I, P, P, D, P, P, I, P, L, L, L, L, L, P, L, L, I]
+        lib.kron_host_apply.restype = None
+        lib.kron_host_apply(kid, p(l), p(ww), amp, p(ncube), p(vox), cb * 3, p(X), N, X.shape[0], 0, N, X.shape[0], p(out), 3 * N, N, 0)
+    else:
+        pad = np.zeros(3, dtype=np.int32)
+        lib.fftconv_host_apply.argtypes = [I, P, P, D, P, P, I, P, L, L, L, L, L, P, L, L, I, P]
+        lib.fftconv_host_apply.restype = None
+        lib.fftconv_host_apply(kid, p(l), p(ww), amp, p(ncube), p(vox), cb * 3, p(X), N, X.shape[0], 0, N, 2, p(out), 3 * N, N, 0, p(pad))
+    assert np.isfinite(out).all()
+    return out.reshape(X.shape[0], 3, N)
 
 
 def _fft_rows(cb, r, X):
@@ -130,10 +162,17 @@ def run(name, structure, workers, rows_per_job):
     pt_path = "/dev/shm/geobo_pts_%s_%d" % (name, os.getpid())
     np.memmap(pt_path, dtype=np.float64, mode="w+", shape=(npanel, M, 3, panel)).flush()
     spectra = {}
+    host_so = None
+    if structure.endswith("-host"):
+        import subprocess
+        import tempfile
+        src = os.path.join(ROOT, "tests", "host_harness", "kron_host.cpp" if structure == "kron-host" else "fftconv_host.cpp")
+        host_so = os.path.join(tempfile.mkdtemp(prefix="geobo_host_"), "harness.so")
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", host_so], check=True)
     if structure == "fft":
         spectra = {(cb, r): fc.spectrum(c, params, w, amp, c.kernelfunc, cb, r) for cb in range(2) for r in range(3)}
     G.update(c=c, A=[Ag, Am], didx=didx, pts=pts, params=params, w=w, amp=amp, Ns=Ns, nd=nd, M=M, N=N, panel=panel, npanel=npanel,
-             pt_path=pt_path, structure=structure, spectra=spectra)
+             pt_path=pt_path, structure=structure, spectra=spectra, host_so=host_so)
     AkA = np.zeros((M, M))
     try:
         t0 = time.perf_counter()
@@ -194,7 +233,8 @@ def run(name, structure, workers, rows_per_job):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("workload", choices=["cfg2", "cfg3", "cfg3e"])
-    ap.add_argument("structure", choices=["kron", "fft"])
+    ap.add_argument("structure", choices=["kron", "fft", "kron-host", "fft-host"],
+                    help="kron / fft: the NumPy restatements; kron-host / fft-host: the device sources compiled for the host")
     ap.add_argument("--workers", type=int, default=max(1, (os.cpu_count() or 2) - 1))
     ap.add_argument("--rows-per-job", type=int, default=16)
     args = ap.parse_args()
