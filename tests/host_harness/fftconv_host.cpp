@@ -5,6 +5,7 @@
 #include "../../geobo_b200/csrc/formulas.cuh"
 #include "../../geobo_b200/csrc/fftconv.cuh"
 
+#include <cmath>
 #include <vector>
 
 // Thread order inside one phase (between two barriers): 0 = ascending, 1 = descending, 2 = odd ids first.  The result must not
@@ -18,7 +19,11 @@ namespace {
 // fft_pass_kernel<MODE><<<ceil(nlines / FFT_LPB), FFT_THREADS>>>
 void run_pass(int mode, const FftGeom& g, const FftPass& q, const cplx* in, const double* mul, cplx* out, const cplx* tw, const double* A, long lda,
               long nrows, double* rows_out, long ldo, int accumulate) {
-    std::vector<cplx> sm((size_t)FFT_LPB * q.P + q.P / 2 + 1);
+    // "shared memory" and the scratch lattices start as NaN: device memory is not zero-initialised, a read of an element no thread
+    // has written would surface as a NaN in the output
+    cplx poison;
+    poison.re = poison.im = std::nan("");
+    std::vector<cplx> sm((size_t)FFT_LPB * q.P + q.P / 2 + 1, poison);
     cplx* tws = sm.data() + FFT_LPB * q.P;
     const long blocks = (q.nlines + FFT_LPB - 1) / FFT_LPB;
     for (long bx = 0; bx < blocks; ++bx) {
@@ -73,7 +78,9 @@ void fftconv_host_apply(int kernel_id, const double* l, const double* w, double 
             tw[a * (FFT_MAXP / 2) + k].im = sin(-2.0 * GB_PI * k / Pa[a]);
         }
     if (B < 1) B = 1;
-    std::vector<cplx> scratch((size_t)B * (2 * g.P3 + (long)g.nyl * g.xN * g.Pz));
+    cplx poison;
+    poison.re = poison.im = std::nan("");
+    std::vector<cplx> scratch((size_t)B * (2 * g.P3 + (long)g.nyl * g.xN * g.Pz), poison);
     cplx* X = scratch.data();
     cplx* Y = X + B * g.P3;
     cplx* Z = Y + B * g.P3;

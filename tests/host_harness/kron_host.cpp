@@ -5,6 +5,7 @@
 #include "../../geobo_b200/csrc/formulas.cuh"
 #include "../../geobo_b200/csrc/kron.cuh"
 
+#include <cmath>
 #include <vector>
 
 // Thread order inside one phase (between two barriers): 0 = ascending, 1 = descending, 2 = odd ids first.  The result must not
@@ -36,7 +37,7 @@ void kron_host_apply(int kernel_id, const double* l, const double* w, double amp
         }
     const KronGeom g = kron_geom(xN, yN, zN, c0, c1);
     // kron_factors_kernel: grid (ceil(FL / 128), 3, 9) x 128 threads
-    std::vector<double> kf(9L * 3 * g.FL);
+    std::vector<double> kf(9L * 3 * g.FL, std::nan(""));
     for (int b = 0; b < 9; ++b)
         for (int axis = 0; axis < 3; ++axis)
             for (int bx = 0; bx < (g.FL + 127) / 128; ++bx)
@@ -47,10 +48,12 @@ void kron_host_apply(int kernel_id, const double* l, const double* w, double amp
     // kron_apply
     const long per_row = 3L * g.nyl * g.XZ;
     const long chunk = chunk_rows < 1 ? 1 : chunk_rows;
-    std::vector<double> T(chunk * per_row);
+    // scratch and "shared memory" start as NaN: device memory is not zero-initialised, a read of an element no thread has written
+    // would surface as a NaN in the output
+    std::vector<double> T(chunk * per_row, std::nan(""));
     const int qtiles = (int)((g.XZ + KRON_YTHREADS * KRON_YQ - 1) / (KRON_YTHREADS * KRON_YQ));
     const int jgroups = (g.nyl + KRON_JT - 1) / KRON_JT;
-    std::vector<double> smem(2L * g.xN * g.zs + 2L * g.FL + 3L * g.FL);
+    std::vector<double> smem(2L * g.xN * g.zs + 2L * g.FL + 3L * g.FL, std::nan(""));
     for (long s0 = 0; s0 < nrows; s0 += chunk) {
         const long n = nrows - s0 < chunk ? nrows - s0 : chunk;
         const long r_stride = n * g.nyl * g.XZ;
