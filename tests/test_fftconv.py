@@ -286,3 +286,22 @@ def test_host_compiled_kernels_reproduce_the_live_reference_fixture(host, monkey
     for n, a in zip(CUBES, cubes):
         assert normwise_err(a, f[n]) < 1e-7, n
     assert abs(ex["logl"] - float(f["logl"])) < 1e-7 * abs(float(f["logl"]))
+
+
+def test_host_compiled_kernels_reproduce_the_committed_vtk_goldens(host, monkeypatch):
+    """Example 1 of the reference (25 x 16 x 16, sparse kernel, M = 1056) with Pt computed by the DEVICE SOURCE of the FFT passes
+    (padded lattice 32 x 64 x 32) inside the oracle's lean pipeline: the committed VTK cubes are reproduced to 2e-7."""
+    from test_compact import _pipeline_with_projection
+    f = load_golden("example1.npz")
+    c = o.make_config(json.loads(str(f["cfg"])))
+
+    def project(params, w, amp, A_list):
+        N = A_list[0].shape[1]
+        Pt, pad = _host_projection(host, c, params, w, amp, A_list, 0, N, 4)
+        assert pad == (32, 64, 32)
+        return Pt[:, :, :N]
+
+    cubes, ex = _pipeline_with_projection(monkeypatch, c, f, project)
+    for n, a in zip(CUBES, cubes):
+        assert normwise_err(a, f["gold_" + n]) < 2e-7, n
+    assert abs(ex["logl"] - float(f["logl"])) < 1e-6
