@@ -122,9 +122,10 @@ def test_gpu_align_drill_vs_reference_fixture(which):
 def test_gpu_align_drill_many_samples_vs_oracle():
     """More samples than one shared-memory tile (1024) and a voxel count that is not a multiple of the block size."""
     from geobo_b200 import config_loader, utils
-    cfg = dict(json.loads(str(load_golden("align_drill.npz")["cfg_small"])), xNcube=13, yNcube=7, zNcube=11)
+    cfg = dict(json.loads(str(load_golden("align_drill.npz")["cfg_small"])), xNcube=13, yNcube=9, zNcube=11)   # 9, not 7: the reference's np.arange centres overshoot at yNcube=7 (8 centres)
     config_loader.load_settings(cfg, make_outpath=False)
     c, vp, shape = _centres(cfg)
+    assert vp.shape[1] == int(np.prod(shape))                       # geometry valid for the reference's centre formula
     rng = np.random.default_rng(5)
     n = 2500
     coord = np.column_stack([rng.uniform(-50, c.xLcube + 50, n), rng.uniform(-50, c.yLcube + 50, n), -rng.uniform(-20, c.zLcube + 20, n)])

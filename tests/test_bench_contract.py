@@ -8,7 +8,7 @@ import sys
 
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, check_subprocess
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
              "dtype", "data", "config", "e2e"}
@@ -17,7 +17,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 def _run(args, env=None, timeout=900):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, timeout=timeout,
                        env=dict(os.environ, **(env or {})))
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    check_subprocess(r)
     return [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
 
 

@@ -91,7 +91,7 @@ def test_int8_multi_flush_paths_match_single_flush(ctx):
     import os
     import subprocess
     import sys
-    from conftest import ROOT
+    from conftest import ROOT, check_subprocess
     code = r'''
 import sys, json, numpy as np
 sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
@@ -110,7 +110,7 @@ np.save(sys.argv[1], np.stack(out))
         with tempfile.NamedTemporaryFile(suffix=".npy") as tf:
             env = dict(os.environ, GEOBO_B200_CHUNK=chunk)
             r = subprocess.run([sys.executable, "-c", code, tf.name], env=env, capture_output=True, text=True, timeout=600)
-            assert r.returncode == 0, r.stderr[-2000:]
+            check_subprocess(r)
             res.append(np.load(tf.name))
     for a, b in zip(res[0], res[1]):
         assert np.abs(a - b).max() <= 1e-11 * np.abs(a).max()
