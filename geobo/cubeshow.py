@@ -1,0 +1,6 @@
+"""Alias of ``geobo_b200.cubeshow`` under the reference's module name (see ``geobo/__init__.py``)."""
+import sys
+
+from geobo_b200 import cubeshow as _impl
+
+sys.modules[__name__] = _impl

@@ -1,0 +1,6 @@
+"""Alias of ``geobo_b200.kernels`` under the reference's module name (see ``geobo/__init__.py``)."""
+import sys
+
+from geobo_b200 import kernels as _impl
+
+sys.modules[__name__] = _impl

@@ -616,7 +616,9 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     set_y_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(p->ydev, M, Mp, p->ysol);
     GB_CUDA(ctx, cudaGetLastError());
     // ---- stationary covariance tables (kernels.create_cov evaluated once per lattice offset)
-    GB_CUDA(ctx, launch_cov_tables(cp, p->n, p->vox, p->tables, s));
+    // a non-finite covariance value is reported like a failed factorisation (info = 1): the reference's dense products spread it
+    // over all of AkA and its Cholesky raises (inversion.py:98-104)
+    GB_CUDA(ctx, launch_cov_tables(cp, p->n, p->vox, p->tables, s, p->info));
     GB_CUDA(ctx, cudaEventRecord(p->ev[1], s));
 
     // ---- opt-in structure-exploiting path: factor lines of the separable exp blocks from the tables

@@ -228,11 +228,12 @@ static gemm::Task make_task(const double* A, long lda, const double* B, long ldb
     return t;
 }
 
-// GEOBO_B200_CHOL_OUTER = panels per outer block (1 = plain right-looking, the default; 4 = two-level blocking: the
-// panels of a 512-wide block are factored left-looking and the trailing matrix is updated once per block with K = 512,
-// which keeps the DMMA pipe busier than four K = 128 updates).  Read on every call (tests switch it in-process).
+// GEOBO_B200_CHOL_OUTER = panels per outer block.  Default 4 = two-level blocking: the panels of a 512-wide block are
+// factored left-looking and the trailing matrix is updated once per block with K = 512, which keeps the DMMA pipe 74 % busy
+// (profiles/r2_chol_outer4_cfg3.ncu-rep; four K = 128 updates: 45 %, every C tile read and written four times).
+// 1 = plain right-looking.  Read on every call (tests switch it in-process).
 static int chol_outer_panels() {
-    int outer = 1;
+    int outer = 4;
     if (const char* ev = getenv("GEOBO_B200_CHOL_OUTER")) { outer = atoi(ev); if (outer < 1 || outer > 16) outer = 1; }
     return outer;
 }
@@ -246,9 +247,21 @@ struct CholLookahead {
     cudaStream_t side = nullptr;
     cudaEvent_t panels = nullptr, b_done = nullptr;
 };
-static CholLookahead la;
+// per device (a process may hold contexts on several devices; streams, events and function attributes are per device)
+static CholLookahead la_dev[64];
+static bool potrf_attr_set[64];
 
-static cudaError_t chol_lookahead_setup() {
+static cudaError_t potrf_attr(int smem) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && potrf_attr_set[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) potrf_attr_set[dev] = true;
+    return e;
+}
+
+static cudaError_t chol_lookahead_setup(CholLookahead& la) {
     la.on = false;
     la.b_pending = false;
     if (const char* ev = getenv("GEOBO_B200_CHOL_LOOKAHEAD")) la.on = atoi(ev) != 0;
@@ -262,17 +275,15 @@ static cudaError_t chol_lookahead_setup() {
 }
 
 cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, cudaStream_t s) {
-    static bool attr_set = false;
     const int smem = (NB * PLD + 64 * 64 + NB) * (int)sizeof(double);
     cudaError_t e;
-    if (!attr_set) {
-        e = cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if ((e = potrf_attr(smem)) != cudaSuccess) return e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    CholLookahead& la = la_dev[dev & 63];
     const int nblk = Mp / NB;
     const int outer = chol_outer_panels();
-    if ((e = chol_lookahead_setup()) != cudaSuccess) return e;
+    if ((e = chol_lookahead_setup(la)) != cudaSuccess) return e;
     for (int ob = 0; ob < nblk; ob += outer) {
         const int o0 = ob * NB, oe = (ob + outer < nblk ? ob + outer : nblk), o1 = oe * NB;
         for (int kb = ob; kb < oe; ++kb) {
@@ -386,12 +397,8 @@ __global__ void chol_pan_finalize_kernel(const double* __restrict__ pan, int nbl
 // stage: [Mp * 128 + 128 * 128] doubles, pan: [2 * Mp / 128] doubles, paninfo: [Mp / 128] ints (all device scratch)
 int chol_factor_dist(gb_ctx* ctx, double* Bm, long ldb, int Mp, int Mtrue, const CholWork& w, double* stage, double* pan, int* paninfo,
                      cudaStream_t s) {
-    static bool attr_set = false;
     const int smem = (NB * PLD + 64 * 64 + NB) * (int)sizeof(double);
-    if (!attr_set) {
-        GB_CUDA(ctx, cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    GB_CUDA(ctx, potrf_attr(smem));
     const int nblk = Mp / NB, nr = ctx->nranks, me = ctx->rank;
     GB_CUDA(ctx, cudaMemsetAsync(pan, 0, (size_t)2 * nblk * sizeof(double), s));
     GB_CUDA(ctx, cudaMemsetAsync(paninfo, 0, (size_t)nblk * sizeof(int), s));

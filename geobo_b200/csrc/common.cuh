@@ -107,7 +107,7 @@ cudaError_t init();
 
 // ---------------------------------------------------------------------------- kernel launchers
 cudaError_t launch_cov_tables(const CovParams& cp, const int64_t ncube[3], const double vox[3], double* tables /*9 x ext*/,
-                              cudaStream_t s);
+                              cudaStream_t s, int* nonfinite = nullptr /* device flag set to 1 if any table value is NaN / inf */);
 cudaError_t launch_lattice_ids(const int64_t ncube[3], int* L, int64_t n_padded, cudaStream_t s);
 cudaError_t launch_create_cov_dense(const CovParams& cp, const double* D2, int64_t n, double* out, cudaStream_t s);
 // tables ([9][ext]) and L ([N]) given: stationary tables + gather (HBM-write bound); null: per-element evaluation

@@ -12,7 +12,7 @@
 #include "formulas.cuh"
 
 // ------------------------------------------------------------------------------------ tables
-__global__ void cov_tables_kernel(CovParams P, int xN, int yN, int zN, double sx, double sy, double sz, double* tables) {
+__global__ void cov_tables_kernel(CovParams P, int xN, int yN, int zN, double sx, double sy, double sz, double* tables, int* nonfinite) {
     const int EX = 2 * xN - 1, EY = 2 * yN - 1, EZ = 2 * zN - 1;
     const long ext = (long)EX * EY * EZ;
     const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -22,13 +22,17 @@ __global__ void cov_tables_kernel(CovParams P, int xN, int yN, int zN, double sx
     const int ex = (int)(t % EX), ey = (int)(t / EX);
     const double D2 = lattice_d2(ex - (xN - 1), ey - (yN - 1), ez - (zN - 1), sx, sy, sz);
     const int cr = blockIdx.y;   // c * 3 + r : row-block c (data side), column-block r (voxel side)
-    tables[(long)cr * ext + e] = cov_value(P, cr / 3, cr % 3, D2);
+    const double v = cov_value(P, cr / 3, cr % 3, D2);
+    tables[(long)cr * ext + e] = v;
+    // a NaN / inf anywhere in kcov poisons the reference's dense Asens3 . kcov . Asens3^T (0 * NaN), so its Cholesky always fails
+    // (inversion.py:98-104) -- also when the block-structured products here would never touch the value (e.g. nd = 0)
+    if (nonfinite && !isfinite(v)) *nonfinite = 1;
 }
 
-cudaError_t launch_cov_tables(const CovParams& cp, const int64_t n[3], const double vox[3], double* tables, cudaStream_t s) {
+cudaError_t launch_cov_tables(const CovParams& cp, const int64_t n[3], const double vox[3], double* tables, cudaStream_t s, int* nonfinite) {
     const long ext = (2 * n[0] - 1) * (2 * n[1] - 1) * (2 * n[2] - 1);
     dim3 grid((unsigned)((ext + 255) / 256), 9);
-    cov_tables_kernel<<<grid, 256, 0, s>>>(cp, (int)n[0], (int)n[1], (int)n[2], vox[0], vox[1], vox[2], tables);
+    cov_tables_kernel<<<grid, 256, 0, s>>>(cp, (int)n[0], (int)n[1], (int)n[2], vox[0], vox[1], vox[2], tables, nonfinite);
     return cudaGetLastError();
 }
 

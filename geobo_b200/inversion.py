@@ -73,18 +73,32 @@ class Inversion:
     # ------------------------------------------------------------------ device problem
     @staticmethod
     def _slices():
-        """Optional settings key ``precision`` (absent in reference YAMLs -> 'fp64'):
-        'fp64'   : projection A.K on the fp64 tensor pipe (DMMA);
+        """Optional settings key ``precision`` (absent in reference YAMLs -> 'auto'):
+        'auto'   : 'int8x5' whenever the cube admits the tensor-core path (zNcube % 16 == 0, e.g. both committed examples),
+                   else 'fp64' -- so an unmodified reference YAML runs on tcgen05 where it can.  int8x5 is the floor: 39-bit
+                   operands keep the (unrefined) variance at <= 3e-7 of its maximum on the full-size fixtures, 31 bits (int8x4)
+                   only reach 8.5e-6, a hair inside the 1e-5 target (profiles/r1_int8_vs_fp64_32cube.log);
+        'fp64'   : projection A.K on the fp64 tensor pipe (DMMA), any cube shape;
         'int8x4' / 'int8x5' / 'int8x6' : exact int8 digit products on tcgen05/TMEM with 31 / 39 / 47 bits per
         operand for the three dense products (A.K, A.Pt^T, L^-1.Pt); the Cholesky stays fp64 and the mean comes from
         ``refine`` (optional key, default 1) steps of iterative refinement against the fp64 matrix-free operator.
-        Needs zNcube % 16 == 0."""
-        prec = str(getattr(_cfg, "precision", "fp64")).lower()
+        Needs zNcube % 16 == 0 (refused loudly otherwise).
+        The environment variable GEOBO_B200_DEFAULT_PRECISION replaces the default for settings without the key."""
+        import os
+        prec = str(getattr(_cfg, "precision", os.environ.get("GEOBO_B200_DEFAULT_PRECISION", "auto"))).lower()
+        if prec == "auto":
+            return 5 if int(_cfg.zNcube) % 16 == 0 else 0
         if prec in ("fp64", "f64", "double"):
             return 0
         if prec in ("int8x4", "int8x5", "int8x6"):
             return int(prec[-1])
-        raise ValueError("settings key 'precision' must be 'fp64', 'int8x4', 'int8x5' or 'int8x6', got %r" % prec)
+        raise ValueError("settings key 'precision' must be 'auto', 'fp64', 'int8x4', 'int8x5' or 'int8x6', got %r" % prec)
+
+    @property
+    def precision_used(self):
+        """'fp64' or 'int8xS': the arithmetic the settings resolve to for this cube."""
+        s = self._slices()
+        return "int8x%d" % s if s else "fp64"
 
     @staticmethod
     def _structure():
@@ -161,11 +175,10 @@ class Inversion:
         """Negative log marginal likelihood for ``[amp, lengthscale factor, w1, w2, w3]`` (``inversion.py:125-152``)."""
         gp_length = params[1] * np.asarray([_cfg.xvoxsize, _cfg.xvoxsize, _cfg.xvoxsize])
         kernel.dedup_lengthscales(gp_length)
-        try:
-            h = self._hyper(gp_length=gp_length, coeffm=np.asarray(params[2:5], dtype=float), gp_amp=params[0])
-            nll, _ = self._problem.neg_logl(h)
-        except Exception:
-            nll = np.inf
+        # numerical failures (non-PD AkA, non-finite result) come back as +inf from the library (inversion.py:150-152); anything else
+        # -- CUDA / NCCL errors, an unsupported configuration -- is a real error and propagates instead of poisoning the optimiser
+        h = self._hyper(gp_length=gp_length, coeffm=np.asarray(params[2:5], dtype=float), gp_amp=params[0])
+        nll, _ = self._problem.neg_logl(h)
         return nll
 
     def optimize_gp(self):

@@ -8,6 +8,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# Settings without a `precision` key resolve to 'auto' in the product (int8x5 where the cube admits it).  The parity tests that
+# say nothing about precision were written against the fp64 path and its tolerances; the tensor-core path has its own tests
+# (test_gpu_int8.py, incl. the 'auto' default), so the suite pins the default of key-less settings to fp64.
+os.environ.setdefault("GEOBO_B200_DEFAULT_PRECISION", "fp64")
 
 # compile command of the host builds of the device sources (tests/host_harness/*.cpp).  GEOBO_B200_HARNESS_CXXFLAGS adds flags:
 # tests/test_host_harness_asan.py re-runs those tests with -fsanitize=address so that an out-of-bounds index in the per-thread

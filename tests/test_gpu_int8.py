@@ -54,6 +54,34 @@ def test_int8_needs_z_multiple_of_16(ctx):
     assert "zNcube" in str(e.value)
 
 
+def test_precision_auto_default_uses_the_tensor_core_path_where_admissible(ctx, monkeypatch):
+    """Settings without a ``precision`` key (every reference YAML): 'auto' = int8x5 when zNcube % 16 == 0 -- the reference's
+    committed example 1 (25 x 16 x 16) then runs on tcgen05 and still reproduces its VTK goldens --, fp64 otherwise."""
+    from geobo_b200 import inversion
+    monkeypatch.delenv("GEOBO_B200_DEFAULT_PRECISION", raising=False)
+    f = load_golden("example1.npz")
+    cfg = configure(f["cfg"])
+    from geobo_b200 import config_loader
+    assert not hasattr(config_loader, "precision")
+    inv, out = run_cubing(f)
+    assert inv.precision_used == "int8x5"
+    launches_int8 = inv.timings["launches"]
+    for n, a in zip(CUBES, out):
+        assert normwise_err(a, f["gold_" + n]) < 1e-6 < TOL_STATED, n
+    configure(f["cfg"], precision="fp64")
+    inv64, out64 = run_cubing(f)
+    assert inv64.precision_used == "fp64" and inv64.timings["launches"] != launches_int8     # a different kernel sequence ran
+    for n, a, b in zip(CUBES, out, out64):
+        assert normwise_err(a, b) < 1e-6, n
+    c = configure(base_cfg(), xNcube=6, yNcube=5, zNcube=12, kernelfunc="exp")
+    assert inversion.Inversion().precision_used == "fp64"                                    # not admissible -> fp64, no refusal
+    f2 = synthetic_inputs(c, 2)
+    ref, _ = o.cubing_lean(c, f2["grav"], f2["mag"], f2["drillfield"], f2["sensor_locations"], f2["drilldata0"])
+    _, out2 = run_cubing(f2)
+    for n, a, r in zip(CUBES, out2, ref):
+        assert normwise_err(a, r) < 1e-7, n
+
+
 def test_int8_full_size_32cube_vs_fp64_path(ctx):
     """BASELINE config 2 size (N = 32768, M = 2048, exp kernel, cond ~ 1e6): slice path against the fp64 DMMA path
     on the same device problem, plus linearity of the mean in the data."""

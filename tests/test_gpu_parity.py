@@ -210,13 +210,15 @@ def test_cubing_odd_shapes_vs_oracle(ctx, shape, kf, nd):
     assert abs(inv.logl - ex["logl"]) < 1e-7 * abs(ex["logl"])
 
 
-def test_two_level_cholesky_flag_vs_oracle(ctx, monkeypatch):
-    """GEOBO_B200_CHOL_OUTER=4: the panels of a 512-wide block are factored left-looking and the trailing matrix is
-    updated once per block (K = 512).  M = 1155 -> 10 panels = two full outer blocks and a ragged one of two panels."""
+@pytest.mark.parametrize("outer", ["1", "3", "4"])
+def test_two_level_cholesky_flag_vs_oracle(ctx, monkeypatch, outer):
+    """GEOBO_B200_CHOL_OUTER (default 4): the panels of a 512-wide block are factored left-looking and the trailing matrix is
+    updated once per block (K = 512).  M = 1155 -> 10 panels = two full outer blocks and a ragged one of two panels;
+    1 = the plain right-looking factorisation, 3 = three full blocks and a single trailing panel."""
     c = configure(base_cfg(), xNcube=24, yNcube=24, zNcube=4, kernelfunc="exp")
     f = synthetic_inputs(c, 3)
     ref, ex = o.cubing_lean(c, f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"])
-    monkeypatch.setenv("GEOBO_B200_CHOL_OUTER", "4")
+    monkeypatch.setenv("GEOBO_B200_CHOL_OUTER", outer)
     inv, out = run_cubing(f)
     for n, a, r in zip(CUBES, out, ref):
         assert normwise_err(a, r) < TOL_CUBE, n
@@ -245,6 +247,18 @@ def test_not_positive_definite_exits_like_reference(ctx, capsys):
     """matern32 with equal scales: 0/0 in the cross term -> Cholesky fails -> two prints + sys.exit(1) (inversion.py:99-104)."""
     c = configure(base_cfg(), xNcube=6, yNcube=5, zNcube=4, kernelfunc="matern32")
     f = synthetic_inputs(c, 2)
+    with pytest.raises(SystemExit) as e:
+        run_cubing(f)
+    assert e.value.code == 1
+    assert "Cholesky decompostion failed" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("prec", ["fp64", "int8x5"])
+def test_non_finite_covariance_without_drill_data_exits_like_reference(ctx, capsys, prec):
+    """matern32 with equal scales and NO drill rows: the block-structured products never touch the NaN cross block (0, 2), but the
+    reference's dense Asens3 . kcov . Asens3^T spreads 0 * NaN over all of AkA, so it always exits (inversion.py:98-104)."""
+    c = configure(base_cfg(), xNcube=6, yNcube=5, zNcube=16, kernelfunc="matern32", precision=prec)
+    f = synthetic_inputs(c, 0)
     with pytest.raises(SystemExit) as e:
         run_cubing(f)
     assert e.value.code == 1

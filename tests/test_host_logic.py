@@ -101,12 +101,31 @@ def _worker(rank, world, port, q):
     full_truth = np.arange(3 * n, dtype=float).reshape(3, n)
     got = dist.allgather_columns(full_truth[:, c0:c1], n)
     mx = dist.max_over_ranks(10.0 + rank)
+    uid = dist.broadcast_bytes(b"id-from-rank-0" if rank == 0 else None)
     dist.barrier()
-    q.put((rank, bool(np.array_equal(got, full_truth)), mx))
+    # the same gather / max through torch.distributed's gloo backend (test infrastructure only: the package itself has no torch)
+    import torch
+    import torch.distributed as td
+    td.init_process_group(backend="gloo", rank=rank, world_size=world)
+    per = dist.shard_columns(n, world, 0)[1]
+    buf = np.zeros((3, per))
+    buf[:, :c1 - c0] = full_truth[:, c0:c1]
+    outs = [torch.zeros((3, per), dtype=torch.float64) for _ in range(world)]
+    td.all_gather(outs, torch.from_numpy(buf))
+    gl = np.empty((3, n))
+    for r in range(world):
+        a0, a1 = dist.shard_columns(n, world, r)
+        gl[:, a0:a1] = outs[r].numpy()[:, :a1 - a0]
+    t = torch.tensor([10.0 + rank], dtype=torch.float64)
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    td.destroy_process_group()
+    dist.shutdown()
+    q.put((rank, bool(np.array_equal(got, full_truth)) and bool(np.array_equal(got, gl)) and uid == b"id-from-rank-0", mx, float(t[0])))
 
 
 def test_two_rank_gloo_gather_and_max():
-    """World-size-2 gloo run of the host-side shard/gather/timing logic used by the multi-GPU path."""
+    """World-size-2 run of the host-side shard / gather / timing logic of the multi-GPU path: the package's own TCP control
+    plane (geobo_b200/dist.py; no torch in the product) next to a gloo process group doing the same gather and max."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -114,7 +133,16 @@ def test_two_rank_gloo_gather_and_max():
     ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in ps:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in ps)
+    res = sorted(q.get(timeout=180) for _ in ps)
     for p in ps:
         p.join(timeout=60)
-    assert res == [(0, True, 11.0), (1, True, 11.0)]
+    assert res == [(0, True, 11.0, 11.0), (1, True, 11.0, 11.0)]
+
+
+def test_package_has_no_torch_import():
+    import re
+    pkg = os.path.join(ROOT, "geobo_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert not re.search(r"^\s*(import|from)\s+torch", src, re.M), name

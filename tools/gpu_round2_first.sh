@@ -8,7 +8,7 @@
 # usage: tools/gpu_round2_first.sh <tag>;  2-GPU follow-up: gpurun --gpus 2 -- 'python -m pytest tests/test_multigpu.py tests/test_kron.py -m gpu -q'
 TAG=${1:-r2a}
 mkdir -p gpurun_out
-timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_gpu_$TAG.log
+timeout 1800 python -m pytest tests -m gpu -q --durations=25 > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -60 gpurun_out/pytest_gpu_$TAG.log
 cat gpurun_out/fullsize_parity.json 2>/dev/null
 timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke_$TAG.log
 timeout 1200 python bench.py > gpurun_out/bench_${TAG}_cfg2.json 2> gpurun_out/bench_${TAG}_cfg2.err; echo "bench rc=$?"; cut -c1-1500 gpurun_out/bench_${TAG}_cfg2.json
