@@ -12,13 +12,26 @@ import numpy as np
 from . import _lib
 from . import config_loader as _cfg
 
-_state = {"drill_rec": None, "drill_var": None}
+_state = {"drill_rec": None, "drill_var": None, "util_key": None, "util": None}
 
 
 def set_cubes(drill_rec, drill_var):
     """The reference reads module globals; set them once after ``Inversion.cubing``."""
     _state["drill_rec"] = np.ascontiguousarray(drill_rec, dtype=float)
     _state["drill_var"] = np.ascontiguousarray(drill_var, dtype=float)
+    _state["util_key"] = _state["util"] = None
+
+
+def _utility_map(rec, var, costs, kappa, beta):
+    """The whole utility map, computed once per (cubes, costs, kappa, beta) and then indexed: as a drop-in ``shgo`` objective
+    ``futility_vertical`` is called point by point, and a full-cube upload + launch + sync per evaluation would be slower than the
+    NumPy original.  Cached by object identity of the arrays (``set_cubes`` invalidates it)."""
+    key = (id(rec), id(var), id(costs), float(kappa), float(beta), rec.shape)
+    if _state["util_key"] != key:
+        _state["util"] = _lib.default_context().acquisition_vertical(rec, var, kappa, beta, costs)
+        _state["util_key"] = key
+        _state["util_refs"] = (rec, var, costs)          # keeps the ids alive while the cache entry exists
+    return _state["util"]
 
 
 def _cubes(drill_rec, drill_var):
@@ -53,8 +66,9 @@ def futility_vertical(params, costs=None, drill_rec=None, drill_var=None, kappa=
     xd, yd = int(np.round(params[0])), int(np.round(params[1]))
     if not (0 < xd < rec.shape[0] - 1 and 0 < yd < rec.shape[1] - 1):
         return np.inf
-    util, _ = sweep_vertical(rec, var, costs, kappa, beta, top=1)
-    return -util[xd, yd]
+    kappa = _cfg.kappa if kappa is None else kappa
+    beta = _cfg.beta if beta is None else beta
+    return -_utility_map(rec, var, costs, kappa, beta)[xd, yd]
 
 
 def futility_drill(params, costs=None, drill_rec=None, drill_var=None, kappa=None, beta=None):

@@ -439,39 +439,122 @@ def calc_logl(c, A_list, didx, y, params5):
 
 
 # --------------------------------------------------------------------------- bounded CPU baseline (bench.py only)
-def cpu_baseline_sample(c, A_list, didx, y, gp_length=None, panel_cols=2048, jchunk=2048, n_jchunks=None, target_seconds=20.0):
-    """Time the lean CPU path of predict3 on a bounded, deterministic sample and scale to the whole cube.
+class TiledSens:
+    """Stand-in for a sensitivity matrix in TIMING runs only: ``nrows`` rows made by repeating a few real rows of ``A_sens``
+    (each scaled by a row factor), materialised chunk by chunk -- the timed stages use it only as a dgemm operand, whose cost
+    does not depend on the values, and a dense (Ns, N) array would be 4.3 GB per survey at 64x64x32."""
 
-    The projection Pt = A.K costs the same for every (column panel, contraction chunk) pair, so it is
-    timed on ONE panel of ``panel_cols`` voxel columns x ``n_jchunks`` evenly spaced contraction chunks of
-    ``jchunk`` voxels (BLAS-efficient shapes, like the full run) and scaled by the pair count.  AkA,
-    the triangular solve and mean/variance are linear in the column count: timed on the panel and
-    scaled by N / panel_cols.  The M x M Cholesky is timed in full on an SPD matrix of the true size.
-    Returns the estimated whole-cube seconds, the per-stage split and the sample description."""
+    def __init__(self, rows, nrows, seed=0):
+        self.rows = np.ascontiguousarray(rows)
+        self.shape = (int(nrows), self.rows.shape[1])
+        self.scale = 1.0 + 0.01 * np.random.default_rng(seed).standard_normal((self.shape[0], 1))
+
+    def __getitem__(self, key):
+        rsel, csel = key
+        assert isinstance(rsel, slice) and rsel == slice(None)
+        sub = self.rows[:, csel]
+        reps = -(-self.shape[0] // sub.shape[0])
+        return np.tile(sub, (reps, 1))[:self.shape[0]] * self.scale
+
+
+def _timing_operands(cfg, gp_length):
+    c = make_config(cfg)
     xN, yN, zN = c.xNcube, c.yNcube, c.zNcube
-    N = xN * yN * zN
-    Ns = A_list[0].shape[0]
-    nd = didx.size
-    M = 2 * Ns + nd
-    gl, sig, w, amp = _gp_setup(c, gp_length)
+    Ns = xN * yN
+    E, _ = cube_geometry(c)
+    loc = sensor_grid(c)
+    rows = np.unique(np.linspace(0, Ns - 1, min(Ns, 8)).astype(int))
+    Ag = TiledSens(a_sens(c, c.magneticField * 0, loc, E, "grav", sensors=list(rows)), Ns, seed=1)
+    Am = TiledSens(a_sens(c, c.magneticField, loc, E, "magn", sensors=list(rows)), Ns, seed=2)
+    gl, sig, w, amp = _gp_setup(c, None if gp_length is None else np.array(gp_length, dtype=float))
     params = dedup_lengths(gl)
     pts = grid_points((xN, yN, zN), (c.xvoxsize, c.yvoxsize, c.zvoxsize))
+    return c, [Ag, Am], params, sig, w, amp, pts
+
+
+def _pair_worker(job):
+    """One worker process of the CPU timing sample: ``n`` (panel, chunk) pairs of the projection with ONE BLAS thread, like the
+    workers of tests/golden/make_fullsize_golden.py.  Returns its per-pair times and kernel-evaluation / dgemm split."""
+    cfg, gp_length, didx, cols, jchunk, jstarts = job
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(1):
+        c, A_list, params, sig, w, amp, pts = _timing_operands(cfg, gp_length)
+        didx = np.asarray(didx, dtype=int)
+        pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=jstarts[:1])     # warm-up pair, not timed
+        timers, times = {}, []
+        for j0 in jstarts:
+            t0 = time.perf_counter()
+            pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, timers=timers, jstarts=[j0])
+            times.append(time.perf_counter() - t0)
+    return times, timers.get("kernel_eval", 0.0), timers.get("dgemm_proj", 0.0)
+
+
+def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=2048, target_seconds=20.0, workers=None):
+    """Time the lean CPU path of predict3 on a bounded, deterministic sample and scale to the whole cube.
+
+    Arrangement = the one that produced the full-size fixtures (tests/golden/make_fullsize_golden.py): the projection Pt = A.K is
+    split into independent (column panel, contraction chunk) pairs handed to ``workers`` processes with one BLAS thread each, so
+    EVERY host core is busy in the single-threaded NumPy ufunc stage (kernel evaluation, 2/3 of the time) as well as in dgemm --
+    more favourable to the CPU than the reference's own single process, where only BLAS is threaded.  All pairs cost the same:
+    each worker times ``n`` pairs one by one; the aggregate rate (sum over workers of pairs / elapsed) is scaled to the
+    pair count of the cube (median / min / max pair time = the spread of the sample).  AkA, the triangular solve and mean /
+    variance are linear in the column count: timed on one panel with all BLAS threads and scaled by N / panel_cols.  The M x M
+    Cholesky is timed in full on an SPD matrix of the true size.  When the whole inversion fits ``target_seconds`` it is run in
+    full instead (single process, BLAS on all threads; ``sample`` says "full").
+    Returns the estimated whole-cube seconds, the per-stage split and the sample description."""
+    import multiprocessing as mp
+    c, A_list, params, sig, w, amp, pts = _timing_operands(cfg, gp_length)
+    xN, yN, zN = c.xNcube, c.yNcube, c.zNcube
+    N = xN * yN * zN
+    Ns = xN * yN
+    didx = np.asarray(didx, dtype=int)
+    nd = didx.size
+    M = 2 * Ns + nd
+    workers = int(workers or 1)
     panel_cols = int(min(N, panel_cols))
     cols = np.arange((N - panel_cols) // 2, (N - panel_cols) // 2 + panel_cols)
     all_j = list(range(0, N, jchunk))
-    if n_jchunks is None:
-        # probe one chunk, then take as many as fit the time budget (the non-projection stages take a share too)
-        t0 = time.perf_counter()
-        pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=all_j[:1])
-        per = max(time.perf_counter() - t0, 1e-3)
-        n_jchunks = int(max(1, min(len(all_j), 0.6 * target_seconds / per)))
-    sel = [all_j[i] for i in np.unique(np.linspace(0, len(all_j) - 1, n_jchunks).astype(int))]
-    timers = {}
+    n_panels = -(-N // panel_cols)
+    # probe one pair (also warms the BLAS threads up; not part of the sample)
     t0 = time.perf_counter()
-    Pt = pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, timers=timers, jstarts=sel)   # (M, 3, panel)
-    t_panel = time.perf_counter() - t0
+    pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=all_j[:1])
+    per = max(time.perf_counter() - t0, 1e-4)
+    if per * len(all_j) * n_panels * 1.3 <= target_seconds:
+        # ---- the whole inversion fits the budget: run it in full
+        A_dense = [A[:, np.arange(N)] for A in A_list]
+        gl = np.array(params, dtype=float)
+        timers = {}
+        t0 = time.perf_counter()
+        mu, var, logl, _ = predict_lean(c, A_dense, didx, y, gl, sig, w, amp, panel=panel_cols, timers=timers)
+        total = time.perf_counter() - t0
+        return dict(seconds_estimated=total, seconds_measured=total,
+                    stages=dict(kernel_eval=timers.get("kernel_eval", 0.0), dgemm_proj=timers.get("dgemm_proj", 0.0), aka=timers["aka"],
+                                chol=timers["chol"], trsm=timers["trsm"], mean_var=timers["mean_var"]),
+                    sample="full: the whole inversion in one process (%d panels of %d voxel columns x %d contraction chunks, AkA, Cholesky "
+                           "M=%d, triangular solve, mean + variance)" % (n_panels, panel_cols, len(all_j), M),
+                    full=True, workers=1, pair_seconds=dict(median=per, min=per, max=per, n=0), checksum=float(np.nansum(mu) + np.nansum(var)))
+    # ---- bounded sample: `workers` processes x n pairs each (under contention a pair is slower than the probe: allow for 2x)
+    n_each = int(max(2, min(len(all_j), 0.5 * target_seconds / (2.0 * per))))
+    jobs = []
+    for wk in range(workers):
+        sel = [all_j[(wk * n_each + i) % len(all_j)] for i in range(n_each)]
+        jobs.append((dict(cfg), None if gp_length is None else list(map(float, gp_length)), didx.tolist(), cols, jchunk, sel))
+    t0 = time.perf_counter()
+    if workers > 1:
+        with mp.get_context("spawn").Pool(workers) as pool:      # spawn: the caller may hold a CUDA context, which must not be forked
+            res = pool.map(_pair_worker, jobs, chunksize=1)
+    else:
+        res = [_pair_worker(jobs[0])]
+    t_wall = time.perf_counter() - t0
+    pair_t = np.concatenate([np.asarray(r[0]) for r in res])
+    rate = sum(len(r[0]) / sum(r[0]) for r in res)               # pairs per second, all workers together
+    k_ev, k_mm = sum(r[1] for r in res), sum(r[2] for r in res)
+    share = k_ev / max(k_ev + k_mm, 1e-12)
     scale_cols = N / panel_cols
-    scale_proj = scale_cols * (len(all_j) / len(sel))
+    n_pairs = scale_cols * len(all_j)
+    t_proj = n_pairs / rate
+    # ---- the other stages on one panel, BLAS on all threads
+    Pt = pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=all_j[:2])      # operand for the timings below
     t0 = time.perf_counter()
     AkA = np.empty((M, M))
     AkA[:Ns] = A_list[0][:, cols] @ Pt[:, 0, :].T
@@ -492,13 +575,16 @@ def cpu_baseline_sample(c, A_list, didx, y, gp_length=None, panel_cols=2048, jch
     mu = V.T @ u
     var = amp - np.einsum("ij,ij->j", V, V)
     t_mv = time.perf_counter() - t0
-    est = t_panel * scale_proj + (t_aka + t_trsm + t_mv) * scale_cols + t_chol
-    return dict(seconds_estimated=est, seconds_measured=t_panel + t_aka + t_chol + t_trsm + t_mv,
-                stages=dict(kernel_eval=timers.get("kernel_eval", 0.0) * scale_proj, dgemm_proj=timers.get("dgemm_proj", 0.0) * scale_proj,
+    est = t_proj + (t_aka + t_trsm + t_mv) * scale_cols + t_chol
+    return dict(seconds_estimated=est, seconds_measured=t_wall + t_aka + t_chol + t_trsm + t_mv,
+                stages=dict(kernel_eval=t_proj * share, dgemm_proj=t_proj * (1.0 - share),
                             aka=t_aka * scale_cols, chol=t_chol, trsm=t_trsm * scale_cols, mean_var=t_mv * scale_cols),
-                sample="projection Pt=A.K timed on 1 panel of %d voxel columns x %d of %d contraction chunks of %d voxels (all %d "
-                       "sensor rows), scaled x%.1f; AkA / triangular solve / mean+variance timed on that panel, scaled x%.1f; "
-                       "Cholesky M=%d timed in full" % (panel_cols, len(sel), len(all_j), jchunk, 2 * Ns, scale_proj, scale_cols, M),
+                sample="projection Pt=A.K: %d worker processes (1 BLAS thread each) x %d (panel of %d voxel columns, chunk of %d contraction voxels) "
+                       "pairs with all %d sensor rows, each pair timed; aggregate %.2f pairs/s scaled to the cube's %.0f pairs; AkA / triangular "
+                       "solve / mean+variance timed on one panel with BLAS on all threads, scaled x%.1f; Cholesky M=%d timed in full"
+                       % (workers, n_each, panel_cols, jchunk, 2 * Ns, rate, n_pairs, scale_cols, M),
+                full=False, workers=workers,
+                pair_seconds=dict(median=float(np.median(pair_t)), min=float(pair_t.min()), max=float(pair_t.max()), n=int(pair_t.size)),
                 checksum=float(np.nansum(mu) + np.nansum(var)))
 
 

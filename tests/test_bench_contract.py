@@ -32,6 +32,24 @@ def test_reference_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"] and cb["unit"] == "voxels/s"
     assert d["e2e"] == {"value": d["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # 16^3 fits the per-step budget: the sample is the whole inversion
+    assert cb["full_inversion"] is True and cb["sample"].startswith("full")
+    # both arms print the same config dict (the driver compares them): it is built by one function from the workload alone
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(bench.WORKLOADS["cfg1b"], "cfg1b")
+
+
+def test_reference_arm_uses_all_host_cores_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use every host core for BLAS and say how many."""
+    lines = _run(["--impl", "reference", "--workload", "cfg1b", "--steps", "1", "--warmup", "0"],
+                 env={"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    d = json.loads(lines[0])
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        ncores = os.cpu_count()
+    assert d["cpu_baseline"]["cores"] == ncores
 
 
 def test_reference_arm_is_silent_on_other_ranks():
@@ -63,5 +81,5 @@ def test_gpu_structured_arm_line(workload, structure):
                   "--no-cpu-baseline"])
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert BASE_KEYS <= set(d) and d["config"]["structure"].startswith(structure) and d["value"] > 0 and d["finite"] and d["info"] == 0
+    assert BASE_KEYS <= set(d) and d["impl_config"]["structure"].startswith(structure) and d["value"] > 0 and d["finite"] and d["info"] == 0
     assert d["roofline"]["bound"] == "hbm" and d["roofline"]["achieved"] > 0 and d["gpu_launches"] > 0
