@@ -306,7 +306,12 @@ struct gb_problem {
     int64_t n[3] = {0, 0, 0};
     double vox[3] = {0, 0, 0};
     int64_t N = 0, Ns = 0, nd = 0, M = 0, Mp = 0;
-    int64_t c0 = 0, c1 = 0, ncol = 0, ncp = 0, ldp = 0;   // local voxel-column shard of Pt
+    int64_t c0 = 0, c1 = 0, ncol = 0, ncp = 0, ldp = 0;   // local voxel-column shard of Pt; ldp = nrp * ncp (set per call)
+    // Property blocks carried through the pipeline.  Without drill data (nd = 0) the reference's third property (drill) comes out
+    // as NaN cubes (inversion.py:213-214: std of an empty array), so its block of Pt / V / mean / variance is never computed here:
+    // nrp = 2 saves a third of the projection, the triangular solve and the variance product.  cap_nrp sizes the buffers: 3 for
+    // cubes small enough for gb_posterior_cov (which needs all three blocks), else nrp.
+    int nrp = 3, cap_nrp = 3;
     int64_t Kp = 0, lda = 0, ext = 0, C0 = 0;
     std::vector<int64_t> drill;
     double* A[2] = {nullptr, nullptr};   // [Ns][lda] sensitivities (grav, magn)
@@ -423,7 +428,10 @@ extern "C" int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* d, gb_probl
     p->ctx = ctx;
     for (int i = 0; i < 3; ++i) { p->n[i] = d->ncube[i]; p->vox[i] = d->voxsize[i]; }
     p->N = N; p->Ns = d->nsens; p->nd = d->ndrill; p->M = 2 * p->Ns + p->nd; p->Mp = round_up(p->M, 128);
-    p->c0 = c0; p->c1 = c1; p->ncol = c1 - c0; p->ncp = round_up(p->ncol, 32); p->ldp = 3 * p->ncp;
+    p->c0 = c0; p->c1 = c1; p->ncol = c1 - c0; p->ncp = round_up(p->ncol, 32);
+    p->cap_nrp = (p->nd == 0 && 3 * N > 46000) ? 2 : 3;
+    p->nrp = p->nd == 0 ? 2 : 3;
+    p->ldp = p->cap_nrp * p->ncp;                          // allocation width; run_predict sets the width of the call
     p->Kp = round_up(N, 32); p->lda = p->Kp + 32;   // multiples of the largest GEMM slab (BK = 32)
     p->ext = (2 * xN - 1) * (2 * yN - 1) * (2 * zN - 1);
     p->C0 = ((yN - 1) * (2 * xN - 1) + (xN - 1)) * (2 * zN - 1) + (zN - 1);
@@ -592,10 +600,14 @@ static gemm::Task mk(const double* A, long lda, const double* B, long ldb, doubl
 }
 
 // Runs the device pipeline up to `stage`: 0 = through Cholesky + u (logl only), 1 = everything.
-static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
+static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blocks = false) {
     gb_ctx* ctx = p->ctx;
     cudaStream_t s = ctx->stream;
     if (!p->have_data) return gb_fail(ctx, GB_ERR_ARG, "gb_predict before gb_problem_set_data");
+    const int nrp = (p->nd == 0 && !all_blocks) ? 2 : 3;
+    if (nrp > p->cap_nrp) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "all three property blocks requested on a problem sized for two");
+    p->nrp = nrp;
+    p->ldp = (int64_t)nrp * p->ncp;
     p->last_full = full;
     p->nlaunch = 0;
     CovParams cp;
@@ -609,8 +621,12 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
     GB_CUDA(ctx, cudaMemsetAsync(p->scal, 0, 4 * sizeof(double), s));
     GB_CUDA(ctx, cudaMemsetAsync(p->info, 0, 4 * sizeof(int), s));
     if (Mp > M) GB_CUDA(ctx, cudaMemsetAsync(p->Pt + M * ldp, 0, (size_t)(Mp - M) * ldp * sizeof(double), s));
+    if (nrp < 3) {   // the drill property without drill data: NaN like the reference's cubes (all-ones bit pattern = quiet NaN)
+        GB_CUDA(ctx, cudaMemsetAsync(p->mu + 2 * ncol, 0xFF, (size_t)ncol * sizeof(double), s));
+        GB_CUDA(ctx, cudaMemsetAsync(p->var + 2 * ncol, 0xFF, (size_t)ncol * sizeof(double), s));
+    }
     if (ncp > ncol)
-        for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < nrp; ++r)
             GB_CUDA(ctx, cudaMemset2DAsync(p->Pt + r * ncp + ncol, ldp * sizeof(double), 0, (ncp - ncol) * sizeof(double), Mp, s));
     GB_CUDA(ctx, cudaMemcpyAsync(p->ydev, p->y_host_pinned, M * sizeof(double), cudaMemcpyHostToDevice, s));
     set_y_kernel<<<(unsigned)((Mp + 255) / 256), 256, 0, s>>>(p->ydev, M, Mp, p->ysol);
@@ -634,9 +650,9 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
                        "vanish outside a window of the voxel grid; use structure = dense");
     // out[s][r * ncp + (j - c0)] (+)= sum_i A[s][i] K_(blk0 + r)[i][j] through the structured form of the blocks
     auto apply_structured = [&](int blk0, const double* A, long lda, long nrows, double* out, long ldo, int accumulate) -> cudaError_t {
-        if (kron) return kron_apply(kg, p->kron_f, blk0, A, lda, nrows, p->kron_T, p->kron_T_doubles, out, ldo, ncp, accumulate, s, &p->nlaunch);
-        if (fft) return fft_apply(fg, p->fft_W, p->fft_tw, blk0, A, lda, nrows, p->fft_scratch, p->fft_B, out, ldo, ncp, accumulate, s, &p->nlaunch);
-        return stencil_apply(sg, p->tables + (long)blk0 * p->ext + p->C0, A, lda, nrows, out, ldo, ncp, accumulate, s, &p->nlaunch);
+        if (kron) return kron_apply(kg, p->kron_f, blk0, A, lda, nrows, p->kron_T, p->kron_T_doubles, out, ldo, ncp, accumulate, s, &p->nlaunch, nrp);
+        if (fft) return fft_apply(fg, p->fft_W, p->fft_tw, blk0, A, lda, nrows, p->fft_scratch, p->fft_B, out, ldo, ncp, accumulate, s, &p->nlaunch, nrp);
+        return stencil_apply(sg, p->tables + (long)blk0 * p->ext + p->C0, A, lda, nrows, out, ldo, ncp, accumulate, s, &p->nlaunch, nrp);
     };
     if (kron) {
         if (h->kernel_id != GB_KERNEL_EXP)
@@ -710,14 +726,14 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         oa.a8[0] = p->a8[0]; oa.a8[1] = p->a8[1]; oa.a_exp[0] = p->a_exp[0]; oa.a_exp[1] = p->a_exp[1];
         oa.t8 = p->t8; oa.t_exp = p->t_exp; oa.L = p->L; oa.Pt = p->Pt;
         oa.ext = p->ext; oa.C0 = p->C0; oa.kp = p->Kp; oa.ldp = ldp; oa.ncp = ncp;
-        oa.Ns = (int)Ns; oa.ncol = (int)ncol; oa.c0 = (int)p->c0;
+        oa.Ns = (int)Ns; oa.ncol = (int)ncol; oa.c0 = (int)p->c0; oa.nr = nrp;
         GB_CUDA(ctx, ozaki_project(oa, S, ctx->sm_count, s));
         p->nlaunch += 2;                  // table slicing (absmax + digits)
     } else {
         gemm::TaskBatch b;
         b.n = 0;
         for (int c = 0; c < 2; ++c)
-            for (int r = 0; r < 3; ++r) {
+            for (int r = 0; r < nrp; ++r) {
                 gemm::Task t = mk(p->A[c], p->lda, p->tables + (long)(c * 3 + r) * p->ext + p->C0, 0,
                                   p->Pt + (long)c * Ns * ldp + r * ncp, ldp, (int)Ns, (int)ncol, (int)p->Kp, 0);
                 t.Lrow = p->L + p->c0;
@@ -842,6 +858,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         ra.c0 = p->c0; ra.ncol = ncol; ra.ncp = ncp;
         ra.n[0] = (int)p->n[0]; ra.n[1] = (int)p->n[1]; ra.n[2] = (int)p->n[2];
         ra.nsplit = 8;
+        ra.nprop = nrp;
         double* rt = p->rf_t;           // t = A3 K A3^T alpha
         double* rr = p->rf_t + Mp;      // residual
         double* rtmp = p->rf_t + 2 * Mp;
@@ -849,7 +866,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
         for (int itr = 0; itr <= nref; ++itr) {
             GB_CUDA(ctx, refine_at_alpha(ra, p->alpha, p->rf_w, s));       // w = A3^T alpha
             if (structured) {                                              // z = K w   (this rank's voxel columns)
-                for (int c = 0; c < 3; ++c)                                // fixed order c = 0, 1, 2: deterministic sums
+                for (int c = 0; c < nrp; ++c)                              // fixed order c = 0, 1, 2: deterministic sums (c = 2: zero weights without drill data)
                     GB_CUDA(ctx, apply_structured(c * 3, p->rf_w + (long)c * p->Kp, p->Kp, 1, p->rf_z, 0, c > 0));
                 p->nlaunch += 2 + (p->nd ? 1 : 0);
             } else {
@@ -863,19 +880,19 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full) {
             GB_CUDA(ctx, refine_apply_inverse(p->Linv, Mp, rr, rtmp, p->alpha, 1, s));   // alpha += L^-T L^-1 r
             p->nlaunch += 4 + (p->nd ? 1 : 0);
         }
-        GB_CUDA(ctx, refine_scatter_mu(p->rf_z, ncp, ncol, p->mu, s));
+        GB_CUDA(ctx, refine_scatter_mu(p->rf_z, ncp, ncol, p->mu, s, nrp));
         if (nref > 0) GB_CUDA(ctx, refine_dot(p->ydev, p->alpha, M, p->scal + 1, s));    // u.u = y^T (AkA)^-1 y with the refined alpha
         GB_CUDA(ctx, ozaki_slice_rows(p->Linv, Mp, Mp, Mp, S, p->l_exp, p->l8, Mp, 128, s));
         GB_CUDA(ctx, ozaki_slice_cols_mean(p->Pt, Mp, ldp, ldp, S, p->b_exp, p->b8, p->alpha, nullptr, ncp, ncol, s));
         GB_CUDA(ctx, ozaki_colsumsq_tri(p->l8, p->l_exp, p->b8, p->b_exp, (int)Mp, ldp, S, p->partial, p->vscratch, ctx->sm_count, s));
         GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
-        GB_CUDA(ctx, ozaki_var_finalize(p->partial, (int)(Mp / 128), ldp, ncp, ncol, h->gp_amp, p->var, s));
+        GB_CUDA(ctx, ozaki_var_finalize(p->partial, (int)(Mp / 128), ldp, ncp, ncol, h->gp_amp, p->var, s, nrp));
         p->nlaunch += 11;                 // u / alpha (2), two dots, mean scatter, 2 x 2 slicing kernels, colsumsq GEMM, variance
     } else if (full) {
         // ---- V = L^-1 Pt (:114) in place, then mean (:115) and variance diagonal (:117)
         GB_CUDA(ctx, chol_forward_solve(p->Bm, Mp, (int)Mp, w, p->Pt, ldp, (int)ldp, p->tmp, s));
         GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
-        dim3 grid((unsigned)((ncp + 255) / 256), 3);
+        dim3 grid((unsigned)((ncp + 255) / 256), (unsigned)nrp);
         mean_var_kernel<<<grid, 256, 0, s>>>(p->Pt, ldp, ncp, ncol, M, p->ysol, h->gp_amp, p->mu, p->var);
         GB_CUDA(ctx, cudaGetLastError());
         p->nlaunch += 2 * (Mp / 128) + 1;
@@ -1014,7 +1031,7 @@ extern "C" int gb_posterior_cov(gb_problem* p, const gb_hyper* h, double* out) {
     if (3 * p->N > 46000) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "dense 3N x 3N posterior covariance refused for N=%lld", (long long)p->N);
     gb_hyper h64 = *h;
     h64.slices = 0;                       // the dense posterior covariance is built from V = L^-1 Pt, which only the fp64 path stores
-    GB_TRY(run_predict(p, &h64, true));
+    GB_TRY(run_predict(p, &h64, true, /*all_blocks=*/true));
     const long n3 = 3 * p->N;
     DevBuf<double> o;
     GB_CUDA(ctx, o.alloc((size_t)n3 * n3));

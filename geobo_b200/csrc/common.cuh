@@ -118,6 +118,9 @@ cudaError_t launch_sqdist(const double* pts, int64_t n, int dim, double* out, cu
 cudaError_t launch_a_sens(int kind, const double B[3], const double* loc, int64_t nsens, const double* edges,
                           const int64_t ncube[3], double mul, double div, double* out, int64_t ld, int sm_count,
                           cudaStream_t s);
+cudaError_t launch_a_sens_range(int kind, const double B[3], const double* loc, int64_t nsens, const double* edges,
+                                const int64_t ncube[3], double mul, double div, double* out, int64_t ld, int iy_begin, int iy_end,
+                                int sm_count, cudaStream_t s);
 cudaError_t launch_cov_function(int kernel_id, int cross, const double* D2, int64_t count, double l1, double l2, double* out,
                                 cudaStream_t s);
 cudaError_t launch_corner_func(int kind, const double* x, const double* y, const double* z, int64_t count, const double B[3],
@@ -136,6 +139,7 @@ struct OzakiArgs {
     double* Pt;
     long ext, C0, kp, ldp, ncp;
     int Ns, ncol, c0;
+    int nr;                  // property blocks computed per data block: 3, or 2 when there is no drill data (block 2 is NaN in the reference)
 };
 int ozaki_tile_n(int slices);
 int ozaki_tile_np(int slices);
@@ -146,6 +150,12 @@ cudaError_t ozaki_slice_rows(const double* A, long rows, long cols, long ld, int
                              cudaStream_t s);
 cudaError_t ozaki_slice_sens(const double* A, long rows, long cols, long ld, int slices, int* exps, uint8_t* out, long kp,
                              cudaStream_t s);
+// the same digit blocks built from column chunks of the operand (sensitivities that are regenerated chunk by chunk instead of
+// being resident): running row maxima over the chunks -> exponents -> digits of one chunk into k steps [ks0, ks0 + cols / 32)
+cudaError_t ozaki_row_absmax_accum(const double* A, long rows, long cols, long ld, double* amax /*[rows], in-out*/, cudaStream_t s);
+cudaError_t ozaki_exps_from_absmax(const double* amax, long rows, int* exps, cudaStream_t s);
+cudaError_t ozaki_slice_rows_range(const double* A, long rows, long cols, long ld, int slices, const int* exps, uint8_t* out, long kp_total,
+                                   int tr, long ks0, cudaStream_t s);
 cudaError_t ozaki_slice_tables(const double* tables, long ext, int slices, int* exps, uint8_t* out, cudaStream_t s);
 cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStream_t s);
 // int8 digit-slice GEMM with both operands in memory (ozaki_gemm.cu)
@@ -159,7 +169,7 @@ cudaError_t ozaki_gemm_store(const uint8_t* a8, const int* a_exp, int a_ksteps, 
                              int b_ksteps, int b_k0, int ksteps, int M, int N, double* C, long ldc, int lower, int slices,
                              int sm_count, cudaStream_t s);
 cudaError_t ozaki_var_finalize(const double* partial, int n_mtile, long ldpart, long ncp, long ncol, double amp, double* var,
-                               cudaStream_t s);
+                               cudaStream_t s, int nr = 3);
 
 // fp64 matrix-free operator pieces for the iterative refinement of alpha and the posterior mean (refine.cu)
 struct RefineArgs {
@@ -170,8 +180,18 @@ struct RefineArgs {
     long Ns, N, lda, Kp, ext, C0, nd, c0, ncol, ncp;
     int n[3];
     int nsplit;
+    int nprop;               // 3, or 2 without drill data: neither the drill data block (c = 2, its weights are zero) nor the drill
+                             // property block (r = 2, NaN in the reference) enters K.w
 };
 cudaError_t refine_at_alpha(const RefineArgs& a, const double* alpha, double* w /*[3][Kp]*/, cudaStream_t s);
+// the same in column chunks (sensitivities regenerated chunk by chunk): partial sums of the chunk's columns [j0, j0 + ncols), then one finish
+cudaError_t refine_at_alpha_chunk(const RefineArgs& a, const double* A0, const double* A1, long ld, long j0, long ncols, const double* alpha,
+                                  cudaStream_t s);
+cudaError_t refine_at_alpha_finish(const RefineArgs& a, const double* alpha, double* w, cudaStream_t s);
+// t (+)= A_c[:, ja : jb) z[c][ja - c0 : jb - c0)  for a column chunk held at A0 / A1 (column ja of the cube = column ja - j0 of the chunk)
+cudaError_t refine_a_z_chunk(const RefineArgs& a, const double* A0, const double* A1, long ld, long j0, long ja, long jb, const double* z,
+                             double* t, int accumulate, cudaStream_t s);
+cudaError_t refine_a_z_drill(const RefineArgs& a, const double* z, double* t, cudaStream_t s);
 int refine_kw_slices(long ncol);
 cudaError_t refine_kw(const RefineArgs& a, const double* w, double* z /*[refine_kw_slices][3][ncp]*/, cudaStream_t s);
 cudaError_t refine_a_z(const RefineArgs& a, const double* z, double* t /*[Mp]*/, cudaStream_t s);
@@ -180,7 +200,7 @@ cudaError_t refine_residual(const double* y, const double* t, const double* alph
 cudaError_t refine_apply_inverse(const double* Linv, long Mp, const double* x, double* tmp, double* out, int accumulate, cudaStream_t s);
 cudaError_t refine_linv_t(const double* Linv, long Mp, const double* x, int xs, double* out, cudaStream_t s);
 cudaError_t refine_dot(const double* a, const double* b, long n, double* out, cudaStream_t s);
-cudaError_t refine_scatter_mu(const double* z, long ncp, long ncol, double* mu, cudaStream_t s);
+cudaError_t refine_scatter_mu(const double* z, long ncp, long ncol, double* mu, cudaStream_t s, int nr = 3);
 
 // Kronecker-structured products with the exp covariance blocks (kron.cu; opt-in, gb_hyper.structure = GB_STRUCTURE_KRON)
 struct KronGeom;
@@ -190,12 +210,12 @@ int kron_supported(const KronGeom& g, char* why, size_t len);
 cudaError_t kron_build_factors(const double* tables, long ext, long C0, const KronGeom& g, double* kf /*[9][3][FL]*/, cudaStream_t s);
 // out[s][r * r_stride_out + (j - c0)] (+)= sum_i A[s][i] * K_(blk0 + r)[i][j]  for rows s < nrows, r = 0..2, voxel columns j of the shard
 cudaError_t kron_apply(const KronGeom& g, const double* kf, int blk0, const double* A, long lda, long nrows, double* T, long T_doubles,
-                       double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch);
+                       double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch, int nr = 3);
 
 // Compact-support (stencil) products with the 'sparse' covariance blocks (stencil.cu; opt-in, GB_STRUCTURE_COMPACT)
 struct StencilGeom;
 cudaError_t stencil_apply(const StencilGeom& g, const double* tab0 /* tables + blk0 * ext + C0 */, const double* A, long lda, long nrows,
-                          double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch);
+                          double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch, int nr = 3);
 
 // Block-Toeplitz (FFT) products with the stationary covariance blocks (fftconv.cu; opt-in, GB_STRUCTURE_FFT, any kernel)
 struct FftGeom;
@@ -207,7 +227,7 @@ cudaError_t fft_build_twiddles(const FftGeom& g, cplx* tw /*[3][FFT_MAXP / 2]: y
 cudaError_t fft_build_spectra(const FftGeom& g, const double* tables, long ext, long C0, const cplx* tw, cplx* X, cplx* Y, double* W /*[9][P3]*/,
                               cudaStream_t s, long* nlaunch);
 cudaError_t fft_apply(const FftGeom& g, const double* W, const cplx* tw, int blk0, const double* A, long lda, long nrows, cplx* scratch, long B,
-                      double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch);
+                      double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch, int nr = 3);
 
 // Cholesky / triangular solve (chol.cu)
 struct CholWork {

@@ -117,7 +117,7 @@ cudaError_t fft_build_spectra(const FftGeom& g, const double* tables, long ext, 
 // out[s][r * r_stride_out + (j - c0)] (+)= sum_i A[s][i] * K_(blk0 + r)[i][j]   for rows s < nrows, r = 0..2, j in [c0, c1)
 // scratch: B * (2 P3 + nyl xN Pz) complex values (X, Y, Z)
 cudaError_t fft_apply(const FftGeom& g, const double* W, const cplx* tw, int blk0, const double* A, long lda, long nrows, cplx* scratch, long B,
-                      double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch) {
+                      double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch, int nr) {
     if (B < 1) return cudaErrorInvalidValue;
     cplx* X = scratch;
     cplx* Y = X + B * g.P3;
@@ -129,7 +129,7 @@ cudaError_t fft_apply(const FftGeom& g, const double* W, const cplx* tw, int blk
         if ((e = launch_pass<1>(g, fft_pass_fwd_z(g, nb), nullptr, nullptr, X, twz, A + s0 * lda, lda, n, nullptr, 0, 0, s, nlaunch)) != cudaSuccess) return e;
         if ((e = launch_pass<0>(g, fft_pass_fwd_x(g, nb), X, nullptr, Y, twx, nullptr, 0, 0, nullptr, 0, 0, s, nlaunch)) != cudaSuccess) return e;
         if ((e = launch_pass<0>(g, fft_pass_fwd_y(g, nb), Y, nullptr, X, twy, nullptr, 0, 0, nullptr, 0, 0, s, nlaunch)) != cudaSuccess) return e;
-        for (int r = 0; r < 3; ++r) {
+        for (int r = 0; r < nr; ++r) {
             if ((e = launch_pass<0>(g, fft_pass_inv_y(g, nb), X, W + (long)(blk0 + r) * g.P3, Y, twy, nullptr, 0, 0, nullptr, 0, 0, s, nlaunch)) != cudaSuccess) return e;
             if ((e = launch_pass<0>(g, fft_pass_inv_x(g, nb), Y, nullptr, Z, twx, nullptr, 0, 0, nullptr, 0, 0, s, nlaunch)) != cudaSuccess) return e;
             if ((e = launch_pass<2>(g, fft_pass_inv_z(g, nb), Z, nullptr, nullptr, twz, nullptr, 0, n, out + s0 * ldo + r * r_stride_out, ldo, accumulate, s,

@@ -76,7 +76,7 @@ cudaError_t kron_build_factors(const double* tables, long ext, long C0, const Kr
 
 // out[s][r * r_stride_out + (j - c0)] (+)= sum_i A[s][i] * K_(blk0 + r)[i][j]   for rows s < nrows, r = 0..2, j in [c0, c1)
 cudaError_t kron_apply(const KronGeom& g, const double* kf, int blk0, const double* A, long lda, long nrows, double* T, long T_doubles,
-                       double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch) {
+                       double* out, long ldo, long r_stride_out, int accumulate, cudaStream_t s, long* nlaunch, int nr) {
     const long per_row = 3L * g.nyl * g.XZ;
     long chunk = T_doubles / per_row;
     if (chunk < 1) return cudaErrorInvalidValue;
@@ -90,7 +90,7 @@ cudaError_t kron_apply(const KronGeom& g, const double* kf, int blk0, const doub
         const long n = nrows - s0 < chunk ? nrows - s0 : chunk;
         const long r_stride = n * g.nyl * g.XZ;
         kron_y_kernel<<<dim3(qtiles, jgroups, (unsigned)n), KRON_YTHREADS, smem_y, s>>>(g, A + s0 * lda, lda, kf, blk0, T, r_stride);
-        kron_zx_kernel<<<dim3((unsigned)g.nyl, (unsigned)n, 3), KRON_ZXTHREADS, smem_zx, s>>>(g, T, r_stride, kf, blk0, out + s0 * ldo, ldo,
+        kron_zx_kernel<<<dim3((unsigned)g.nyl, (unsigned)n, (unsigned)nr), KRON_ZXTHREADS, smem_zx, s>>>(g, T, r_stride, kf, blk0, out + s0 * ldo, ldo,
                                                                                                  r_stride_out, accumulate);
         if (nlaunch) *nlaunch += 2;
     }

@@ -122,6 +122,7 @@ struct Params {
     double* Pt;               // [Mp][ldp]
     long ext, C0, kp, ldp, ncp;
     int Ns, ncol, c0, chunk;  // chunk: contraction indices per accumulator flush (multiple of 32)
+    int nr;                   // property blocks per data block (3, or 2 without drill data): task t = (c = t / nr, r = t % nr)
     int n_stile, n_itile;     // sensor-row tiles of NT, voxel-column tiles of 128
 };
 
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
     const uint32_t tmem_base = tmem_base_s;
 
     const long tiles_per_task = (long)P.n_stile * P.n_itile;
-    const long ntiles = 6 * tiles_per_task;
+    const long ntiles = 2 * P.nr * tiles_per_task;
     const int ksteps = (int)(P.kp / 32);
     const int chunk_steps = P.chunk / 32;
 
@@ -180,7 +181,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
         const int C0 = (int)P.C0;
         uint32_t it_tile0 = 0;
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it_tile0 += (uint32_t)ksteps) {
-            const int task = (int)(tile / tiles_per_task);            // c * 3 + r
+            const int tq = (int)(tile / tiles_per_task);
+            const int task = (tq / P.nr) * 3 + tq % P.nr;             // c * 3 + r
             const int itile = (int)((tile % tiles_per_task) % P.n_itile);
             const int i0 = itile * 128 + 32 * q4 + (lane & 16);       // first voxel column of this half-warp's segment
             const uint8_t* t8 = P.t8 + (size_t)task * S * plane;
@@ -259,9 +261,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
         if (lane == 0) {
             uint32_t it = 0;
             for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int task = (int)(tile / tiles_per_task);
+                const int tq = (int)(tile / tiles_per_task);
                 const int stile = (int)((tile % tiles_per_task) / P.n_itile);
-                const uint8_t* src = P.a8[task / 3] + (size_t)stile * ksteps * B_BYTES;
+                const uint8_t* src = P.a8[tq / P.nr] + (size_t)stile * ksteps * B_BYTES;
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int st = (int)(it % SB);
                     mbar_wait(&done_bar[st], ((it / SB) & 1) ^ 1);
@@ -320,10 +322,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
         uint32_t chunk_id = 0;
         const int m = warp * 32 + lane;                   // row of D = voxel column inside the tile
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int task = (int)(tile / tiles_per_task);
+            const int tq = (int)(tile / tiles_per_task);
             const long rem = tile % tiles_per_task;
             const int stile = (int)(rem / P.n_itile), itile = (int)(rem % P.n_itile);
-            const int c = task / 3, r = task % 3;
+            const int c = tq / P.nr, r = tq % P.nr, task = c * 3 + r;
             const int s0 = stile * NT, i = itile * 128 + m;
             const bool col_ok = i < P.ncol;
             // result = 2^(eA + eK - 14 - 8 (S-1)) * sum_l acc_l 2^(8 (S-1-l))
@@ -372,7 +374,7 @@ static cudaError_t launch_one(const Params& P, int sm_count, cudaStream_t s) {
     Params q = P;
     q.n_stile = (P.Ns + NT - 1) / NT;
     q.n_itile = (P.ncol + 127) / 128;
-    const long ntiles = 6L * q.n_stile * q.n_itile;
+    const long ntiles = 2L * q.nr * q.n_stile * q.n_itile;
     const int grid = (int)(ntiles < (long)sm_count ? ntiles : (long)sm_count);
     ozaki_project_kernel<S><<<grid, TS_THREADS, smem, s>>>(q);
     return cudaGetLastError();
@@ -442,6 +444,7 @@ cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStre
     P.t8 = a.t8; P.t_exp = a.t_exp; P.L = a.L; P.Pt = a.Pt;
     P.ext = a.ext; P.C0 = a.C0; P.kp = a.kp; P.ldp = a.ldp; P.ncp = a.ncp;
     P.Ns = a.Ns; P.ncol = a.ncol; P.c0 = a.c0;
+    P.nr = a.nr == 2 ? 2 : 3;
     P.chunk = ozaki_chunk();
     P.n_stile = 0;
     P.n_itile = 0;

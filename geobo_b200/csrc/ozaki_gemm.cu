@@ -392,8 +392,8 @@ cudaError_t ozaki_gemm_store(const uint8_t* a8, const int* a_exp, int a_ksteps, 
     return cudaErrorInvalidValue;
 }
 
-cudaError_t ozaki_var_finalize(const double* partial, int n_mtile, long ldpart, long ncp, long ncol, double amp, double* var, cudaStream_t s) {
-    dim3 grid((unsigned)((ncol + 255) / 256), 3);
+cudaError_t ozaki_var_finalize(const double* partial, int n_mtile, long ldpart, long ncp, long ncol, double amp, double* var, cudaStream_t s, int nr) {
+    dim3 grid((unsigned)((ncol + 255) / 256), (unsigned)nr);
     ozaki::var_finalize_kernel<<<grid, 256, 0, s>>>(partial, n_mtile, ldpart, ncp, ncol, amp, var);
     return cudaGetLastError();
 }

@@ -55,6 +55,9 @@ __global__ void w_drill_kernel(const double* __restrict__ alpha_drill, const int
 // per 4 FMAs).  The 16 segments of a block visit the contraction columns in a ROTATED order (cj = sweep index + own
 // column) so that at any moment they all need the SAME lattice offset, i.e. the same table stretch: the table loads of a
 // warp coalesce to one stretch and stay in L1 instead of each output column streaming all nine tables from L2.
+// NB = 3, or 2 without drill data: the drill data block c = 2 has zero weights and the drill property block r = 2 is NaN in the
+// reference, so only the four survey blocks are swept (4/9 of the table FMAs).
+template <int NB>
 __global__ void __launch_bounds__(256) kw_kernel(const double* __restrict__ tables, long ext, long C0, int xN, int yN, int zN,
                                                  const double* __restrict__ w, long Kp, long c0, long nseg, double* __restrict__ z,
                                                  long ncp) {
@@ -75,6 +78,7 @@ __global__ void __launch_bounds__(256) kw_kernel(const double* __restrict__ tabl
     for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[r][q] = 0.0;
+    if (NB == 3) {
     for (int sw = sw0; sw < sw1; ++sw) {
         int cj = sw + ci;
         if (cj >= ncolumns) cj -= ncolumns;
@@ -104,13 +108,39 @@ __global__ void __launch_bounds__(256) kw_kernel(const double* __restrict__ tabl
             }
         }
     }
+    } else {
+    for (int sw = sw0; sw < sw1; ++sw) {
+        int cj = sw + ci;
+        if (cj >= ncolumns) cj -= ncolumns;
+        const int lcj = (cj / xN) * (2 * xN - 1) + cj % xN;
+        const long base = C0 + (long)(lcj - lci) * zs - iz0;
+        const double* wc = w + (long)cj * zN;
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 2; ++c) {
+            const double* wv = wc + (long)c * Kp;
+            const double* t0 = tables + (long)(c * 3 + 0) * ext + base;
+            const double* t1 = tables + (long)(c * 3 + 1) * ext + base;
+            double a1 = __ldg(t0 - 1), a2 = __ldg(t0 - 2), a3 = __ldg(t0 - 3);
+            double b1 = __ldg(t1 - 1), b2 = __ldg(t1 - 2), b3 = __ldg(t1 - 3);
+#pragma unroll 4
+            for (int jz = 0; jz < zN; ++jz) {
+                const double x = __ldg(wv + jz);
+                const double a0 = __ldg(t0 + jz), b0 = __ldg(t1 + jz);
+                acc[0][0] = fma(a0, x, acc[0][0]); acc[0][1] = fma(a1, x, acc[0][1]); acc[0][2] = fma(a2, x, acc[0][2]); acc[0][3] = fma(a3, x, acc[0][3]);
+                acc[1][0] = fma(b0, x, acc[1][0]); acc[1][1] = fma(b1, x, acc[1][1]); acc[1][2] = fma(b2, x, acc[1][2]); acc[1][3] = fma(b3, x, acc[1][3]);
+                a3 = a2; a2 = a1; a1 = a0;
+                b3 = b2; b2 = b1; b1 = b0;
+            }
+        }
+    }
+    }
+#pragma unroll
+    for (int r = 0; r < NB; ++r)
 #pragma unroll
         for (int q = 0; q < 4; ++q) red[dg][tid & 63][r * 4 + q] = acc[r][q];
     __syncthreads();
-    for (int o = tid; o < 64 * 12; o += 256) {
-        const int lq = o / 12, rq = o % 12, r = rq >> 2, q = rq & 3;
+    for (int o = tid; o < 64 * 4 * NB; o += 256) {
+        const int lq = o / (4 * NB), rq = o % (4 * NB), r = rq >> 2, q = rq & 3;
         const long sg = (long)blockIdx.x * 16 + (lq >> 2);
         if (sg < nseg)      // fixed order over the four sweep groups: deterministic
             z[(long)r * ncp + sg * 16 + (lq & 3) * 4 + q] = (red[0][lq][rq] + red[1][lq][rq]) + (red[2][lq][rq] + red[3][lq][rq]);
@@ -242,7 +272,8 @@ cudaError_t refine_kw(const RefineArgs& a, const double* w, double* z, cudaStrea
     const unsigned nbx = (unsigned)((nseg + 15) / 16);
     const int nslice = refine_kw_slices(a.ncol);
     dim3 grid(nbx, (unsigned)nslice);
-    kw_kernel<<<grid, 256, 0, s>>>(a.tables, a.ext, a.C0, a.n[0], a.n[1], a.n[2], w, a.Kp, a.c0, nseg, z, a.ncp);
+    if (a.nprop == 2) kw_kernel<2><<<grid, 256, 0, s>>>(a.tables, a.ext, a.C0, a.n[0], a.n[1], a.n[2], w, a.Kp, a.c0, nseg, z, a.ncp);
+    else kw_kernel<3><<<grid, 256, 0, s>>>(a.tables, a.ext, a.C0, a.n[0], a.n[1], a.n[2], w, a.Kp, a.c0, nseg, z, a.ncp);
     if (nslice > 1) kw_reduce_kernel<<<(unsigned)((3 * a.ncp + 255) / 256), 256, 0, s>>>(z, 3 * a.ncp, nslice);
     return cudaGetLastError();
 }
@@ -277,8 +308,8 @@ cudaError_t refine_dot(const double* a, const double* b, long n, double* out, cu
     return cudaGetLastError();
 }
 
-cudaError_t refine_scatter_mu(const double* z, long ncp, long ncol, double* mu, cudaStream_t s) {
-    dim3 grid((unsigned)((ncol + 255) / 256), 3);
+cudaError_t refine_scatter_mu(const double* z, long ncp, long ncol, double* mu, cudaStream_t s, int nr) {
+    dim3 grid((unsigned)((ncol + 255) / 256), (unsigned)nr);
     scatter_mu_kernel<<<grid, 256, 0, s>>>(z, ncp, ncol, mu);
     return cudaGetLastError();
 }

@@ -11,19 +11,21 @@
 template <int KIND>
 __global__ void __launch_bounds__(256) a_sens_kernel(const double* __restrict__ edges, const double* __restrict__ loc,
                                                      int xN, int yN, int zN, int rows_per_cta, double bx, double by,
-                                                     double bz, double mul, double div, double* __restrict__ out, long ld) {
+                                                     double bz, double mul, double div, double* __restrict__ out, long ld,
+                                                     int iy_begin, int iy_end) {
+    // voxel rows [iy_begin, iy_end) only (a column chunk of the matrix: the voxel index is y-major); out holds those columns
     extern __shared__ double planes[];   // [2][(xN+1)*(zN+1)]
     const int n = blockIdx.x;
-    const int iy0 = blockIdx.y * rows_per_cta;
-    const int iy1 = min(yN, iy0 + rows_per_cta);
-    if (iy0 >= yN) return;
+    const int iy0 = iy_begin + blockIdx.y * rows_per_cta;
+    const int iy1 = min(iy_end, iy0 + rows_per_cta);
+    if (iy0 >= iy_end) return;
     const int px = xN + 1, pz = zN + 1, plane = px * pz;
     const long nedge = (long)(yN + 1) * plane;
     const double* xE = edges;
     const double* yE = edges + nedge;
     const double* zE = edges + 2 * nedge;
     const double lx = loc[3 * n + 0], ly = loc[3 * n + 1], lz = loc[3 * n + 2];
-    double* orow = out + (long)n * ld;
+    double* orow = out + (long)n * ld - (long)iy_begin * xN * zN;
 
     for (int j = iy0; j <= iy1; ++j) {
         double* cur = planes + (j & 1) * plane;
@@ -56,7 +58,16 @@ __global__ void __launch_bounds__(256) a_sens_kernel(const double* __restrict__ 
 
 cudaError_t launch_a_sens(int kind, const double B[3], const double* loc, int64_t nsens, const double* edges,
                           const int64_t n[3], double mul, double div, double* out, int64_t ld, int sm_count, cudaStream_t s) {
-    const int xN = (int)n[0], yN = (int)n[1], zN = (int)n[2];
+    return launch_a_sens_range(kind, B, loc, nsens, edges, n, mul, div, out, ld, 0, (int)n[1], sm_count, s);
+}
+
+// columns of voxel rows [iy_begin, iy_end) only: out[sensor * ld + (j - iy_begin * xN * zN)]
+cudaError_t launch_a_sens_range(int kind, const double B[3], const double* loc, int64_t nsens, const double* edges,
+                                const int64_t n[3], double mul, double div, double* out, int64_t ld, int iy_begin, int iy_end,
+                                int sm_count, cudaStream_t s) {
+    const int xN = (int)n[0], zN = (int)n[2];
+    const int yN = iy_end - iy_begin;          // rows of this launch
+    if (iy_begin < 0 || iy_end > (int)n[1] || yN < 1) return cudaErrorInvalidValue;
     const size_t smem = (size_t)2 * (xN + 1) * (zN + 1) * sizeof(double);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     // enough CTAs to fill the machine a few times over; each extra chunk re-evaluates one plane
@@ -70,11 +81,11 @@ cudaError_t launch_a_sens(int kind, const double B[3], const double* loc, int64_
     if (kind == GB_SENS_GRAV) {
         e = cudaFuncSetAttribute(a_sens_kernel<GB_SENS_GRAV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        a_sens_kernel<GB_SENS_GRAV><<<grid, 256, smem, s>>>(edges, loc, xN, yN, zN, rows, B[0], B[1], B[2], mul, div, out, ld);
+        a_sens_kernel<GB_SENS_GRAV><<<grid, 256, smem, s>>>(edges, loc, xN, (int)n[1], zN, rows, B[0], B[1], B[2], mul, div, out, ld, iy_begin, iy_end);
     } else {
         e = cudaFuncSetAttribute(a_sens_kernel<GB_SENS_MAGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        a_sens_kernel<GB_SENS_MAGN><<<grid, 256, smem, s>>>(edges, loc, xN, yN, zN, rows, B[0], B[1], B[2], mul, div, out, ld);
+        a_sens_kernel<GB_SENS_MAGN><<<grid, 256, smem, s>>>(edges, loc, xN, (int)n[1], zN, rows, B[0], B[1], B[2], mul, div, out, ld, iy_begin, iy_end);
     }
     return cudaGetLastError();
 }

@@ -66,7 +66,7 @@ GB_HD StencilGeom stencil_geom(long xN, long yN, long zN, long c0, long c1, cons
 // block.  tab0: zero offset of the first of the three tables (tables + blk0 * ext + C0); row: output row (already offset to
 // the data row), block r at row + r * r_stride_out, voxel column j at [j - c0].
 GB_HD void stencil_item(const StencilGeom& g, const double* Arow, const double* tab0, int jy, long item, double* row, long r_stride_out,
-                        int accumulate) {
+                        int accumulate, int nr = 3) {
     const int nstrip = (g.zN + STENCIL_W - 1) / STENCIL_W;
     if (item >= (long)g.xN * nstrip) return;
     const int jx = (int)(item / nstrip), z0 = (int)(item % nstrip) * STENCIL_W;
@@ -114,6 +114,7 @@ GB_HD void stencil_item(const StencilGeom& g, const double* Arow, const double* 
         if (j < g.c0 || j >= g.c1) continue;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
+            if (r >= nr) continue;                       // without drill data only the first nr = 2 property blocks are stored
             double* o = row + r * r_stride_out + (j - g.c0);
             *o = accumulate ? *o + acc[r][t] : acc[r][t];
         }

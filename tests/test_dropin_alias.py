@@ -40,9 +40,8 @@ def test_star_import_of_settings_through_the_alias():
 
 DRIVER = r'''
 import sys, json, numpy as np
-sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
-from conftest import load_golden
-f = load_golden("example1.npz")
+sys.path.insert(0, %(root)r)
+f = np.load(%(root)r + "/tests/golden/example1.npz")      # (not through tests/conftest.py: it pins the suite's default precision)
 import geobo_b200.config_loader as _cl
 _cl.load_settings(json.loads(str(f["cfg"])), make_outpath=False)
 # ---- the reference driver's own lines (geobo/run_geobo.py:385-415), imports unedited

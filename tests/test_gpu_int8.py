@@ -73,9 +73,9 @@ def test_precision_auto_default_uses_the_tensor_core_path_where_admissible(ctx, 
     assert inv64.precision_used == "fp64" and inv64.timings["launches"] != launches_int8     # a different kernel sequence ran
     for n, a, b in zip(CUBES, out, out64):
         assert normwise_err(a, b) < 1e-6, n
-    c = configure(base_cfg(), xNcube=6, yNcube=5, zNcube=12, kernelfunc="exp")
+    c = configure(base_cfg(), xNcube=7, yNcube=5, zNcube=12, kernelfunc="exp")
     assert inversion.Inversion().precision_used == "fp64"                                    # not admissible -> fp64, no refusal
-    f2 = synthetic_inputs(c, 2)
+    f2 = synthetic_inputs(c, 3)
     ref, _ = o.cubing_lean(c, f2["grav"], f2["mag"], f2["drillfield"], f2["sensor_locations"], f2["drilldata0"])
     _, out2 = run_cubing(f2)
     for n, a, r in zip(CUBES, out2, ref):
