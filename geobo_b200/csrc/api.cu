@@ -5,6 +5,8 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kron.cuh"
 #include "stencil.cuh"
@@ -314,7 +316,19 @@ struct gb_problem {
     int nrp = 3, cap_nrp = 3;
     int64_t Kp = 0, lda = 0, ext = 0, C0 = 0;
     std::vector<int64_t> drill;
-    double* A[2] = {nullptr, nullptr};   // [Ns][lda] sensitivities (grav, magn)
+    double* A[2] = {nullptr, nullptr};   // [Ns][lda] sensitivities (grav, magn); null in lean mode
+    // Lean mode (large cubes: 2 Ns N doubles are 65 GB at 96x96x48, 275 GB at 128x128x64): the fp64 sensitivities are NOT
+    // resident.  Only their int8 digit blocks are kept (the operands of the tensor-core products); every fp64 pass over them --
+    // digit extraction, A3^T alpha and A3 z of the refinement, gb_forward -- regenerates them in column chunks (voxel rows
+    // [y0, y1) of the cube: the voxel index is y-major) with a_sens_kernel, which costs about as much as reading them from HBM.
+    bool lean = false;
+    double* edges_dev = nullptr;         // [3][(yN+1)(xN+1)(zN+1)] (kept in lean mode)
+    double* loc_dev = nullptr;           // [Ns][3]
+    double Bfield[3] = {0, 0, 0};
+    double grav_mul = 1, grav_div = 1, magn_mul = 1, magn_div = 1;
+    double* Achunk[2] = {nullptr, nullptr};   // [Ns][chunk_ld] one column chunk of each survey
+    int64_t chunk_y = 0, chunk_ld = 0;   // voxel rows per chunk, leading dimension of the chunk buffers
+    double* a_amax = nullptr;            // [2][Ns] running row maxima (digit exponents of rows that are never resident as a whole)
     int* L = nullptr;                    // [Kp] extended-lattice ids
     int64_t* drill_dev = nullptr;
     double* tables = nullptr;            // [9][ext]
@@ -390,6 +404,7 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
     void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
                     p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp,
                     p->Linv, p->tmpL, p->alpha, p->l8, p->l_exp, p->b8, p->b_exp, p->partial,
+                    p->edges_dev, p->loc_dev, p->Achunk[0], p->Achunk[1], p->a_amax,
                     p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch, p->chol_stage, p->chol_pan, p->chol_paninfo, p->kron_f, p->kron_T, p->fft_W, p->fft_tw, p->fft_scratch,
                     p->linv, p->scal, p->info, p->mu, p->var};
     for (void* q : ptrs)
@@ -403,6 +418,32 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
 }
 
 extern "C" uint64_t gb_problem_device_bytes(gb_problem* p) { return p ? p->bytes : 0; }
+
+// both sensitivity matrices for the voxel rows [y0, y1): out_c[s * ld + (j - y0 xN zN)]   (inversion.py:223-224; gravity is called
+// with magneticField * 0)
+static cudaError_t sens_generate(gb_problem* p, int y0, int y1, double* out_g, double* out_m, int64_t ld) {
+    gb_ctx* ctx = p->ctx;
+    const double zeroB[3] = {0.0, 0.0, 0.0};
+    cudaError_t e = launch_a_sens_range(GB_SENS_GRAV, zeroB, p->loc_dev, p->Ns, p->edges_dev, p->n, p->grav_mul, p->grav_div, out_g, ld, y0, y1,
+                                        ctx->sm_count, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return launch_a_sens_range(GB_SENS_MAGN, p->Bfield, p->loc_dev, p->Ns, p->edges_dev, p->n, p->magn_mul, p->magn_div, out_m, ld, y0, y1,
+                               ctx->sm_count, ctx->stream);
+}
+
+// lean mode: f(j0, ncols) for every column chunk, with the chunk's columns [j0, j0 + ncols) regenerated in p->Achunk[0 / 1]
+template <typename F>
+static int lean_for_each_chunk(gb_problem* p, F f) {
+    gb_ctx* ctx = p->ctx;
+    const int64_t XZ = p->n[0] * p->n[2], yN = p->n[1];
+    for (int64_t y0 = 0; y0 < yN; y0 += p->chunk_y) {
+        const int64_t y1 = std::min<int64_t>(yN, y0 + p->chunk_y);
+        GB_CUDA(ctx, sens_generate(p, (int)y0, (int)y1, p->Achunk[0], p->Achunk[1], p->chunk_ld));
+        p->nlaunch += 2;
+        GB_CUDA(ctx, f(y0 * XZ, (y1 - y0) * XZ));
+    }
+    return GB_OK;
+}
 
 extern "C" int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* d, gb_problem** out) {
     if (!ctx || !d || !out) return gb_fail(ctx, GB_ERR_ARG, "gb_problem_create: null argument");
@@ -452,8 +493,37 @@ extern "C" int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* d, gb_probl
     for (auto& e : p->ev) PCUDA(cudaEventCreate(&e));
     p->ev_ok = true;
     memset(p->ms, 0, sizeof p->ms);
-    PCUDA(dev_alloc(p, &p->A[0], (size_t)p->Ns * p->lda, true));
-    PCUDA(dev_alloc(p, &p->A[1], (size_t)p->Ns * p->lda, true));
+    {
+        // lean mode: GEOBO_B200_LEAN_A = 1 / 0 forces it on / off; default: when the two matrices would take more than a fifth of
+        // the device memory (they are 8.6 GB at 64x64x32 -- resident --, 65 GB at 96x96x48 -- lean)
+        size_t fr = 0, tot = 0;
+        PCUDA(cudaMemGetInfo(&fr, &tot));
+        const size_t a_bytes = (size_t)2 * p->Ns * p->lda * sizeof(double);
+        p->lean = a_bytes > tot / 5;
+        if (const char* ev = getenv("GEOBO_B200_LEAN_A")) p->lean = atoi(ev) != 0;
+    }
+    if (!p->lean) {
+        PCUDA(dev_alloc(p, &p->A[0], (size_t)p->Ns * p->lda, true));
+        PCUDA(dev_alloc(p, &p->A[1], (size_t)p->Ns * p->lda, true));
+    } else {
+        // chunk = cy voxel rows; cy * xN * zN must be a multiple of 32 (k steps of the digit blocks), budget per survey
+        // GEOBO_B200_LEAN_CHUNK_MB (default 2048)
+        const int64_t XZ = xN * zN;
+        int64_t unit = 1;
+        while ((unit * XZ) % 32 != 0) unit *= 2;
+        long mb = 2048;
+        if (const char* ev = getenv("GEOBO_B200_LEAN_CHUNK_MB")) mb = atol(ev) > 0 ? atol(ev) : mb;
+        int64_t cy = ((int64_t)mb << 20) / (int64_t)sizeof(double) / (p->Ns * XZ);
+        if (const char* ev = getenv("GEOBO_B200_LEAN_CHUNK_ROWS")) cy = atol(ev);     // voxel rows per chunk (tests: several ragged chunks)
+        cy = cy / unit * unit;
+        if (cy < unit) cy = unit;
+        if (cy > yN) cy = yN;
+        p->chunk_y = cy;
+        p->chunk_ld = round_up(cy * XZ, 32);
+        PCUDA(dev_alloc(p, &p->Achunk[0], (size_t)p->Ns * p->chunk_ld, true));
+        PCUDA(dev_alloc(p, &p->Achunk[1], (size_t)p->Ns * p->chunk_ld, true));
+        PCUDA(dev_alloc(p, &p->a_amax, (size_t)2 * p->Ns, true));
+    }
     PCUDA(dev_alloc(p, &p->L, (size_t)p->Kp, false));
     PCUDA(dev_alloc(p, &p->drill_dev, (size_t)p->nd + 1, false));
     PCUDA(dev_alloc(p, &p->tables, (size_t)9 * p->ext, false));
@@ -476,21 +546,19 @@ extern "C" int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* d, gb_probl
     // sensitivities (inversion.py:223-224) computed on the device; edges/locations are the only H2D traffic
     {
         const int64_t nedge = (xN + 1) * (yN + 1) * (zN + 1);
-        // scratch from the context's cache (a plain cudaMalloc / cudaFree pair per problem costs a device synchronisation)
-        struct Scratch {
-            gb_ctx* c; double* p = nullptr;
-            explicit Scratch(gb_ctx* c_) : c(c_) {}
-            cudaError_t alloc(size_t n) { return gb_dev_malloc(c, (void**)&p, n * sizeof(double)); }
-            ~Scratch() { gb_dev_free(c, p); }
-        } e(ctx), l(ctx);
-        PCUDA(e.alloc(3 * nedge));
-        PCUDA(l.alloc(3 * p->Ns));
-        PCUDA(cudaMemcpyAsync(e.p, d->edges, 3 * nedge * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        PCUDA(cudaMemcpyAsync(l.p, d->locations, 3 * p->Ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        PCUDA(dev_alloc(p, &p->edges_dev, (size_t)3 * nedge, false));
+        PCUDA(dev_alloc(p, &p->loc_dev, (size_t)3 * p->Ns, false));
+        for (int i = 0; i < 3; ++i) p->Bfield[i] = d->magnetic_field[i];
+        p->grav_mul = d->grav_mul; p->grav_div = d->grav_div; p->magn_mul = d->magn_mul; p->magn_div = d->magn_div;
+        PCUDA(cudaMemcpyAsync(p->edges_dev, d->edges, 3 * nedge * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        PCUDA(cudaMemcpyAsync(p->loc_dev, d->locations, 3 * p->Ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         PCUDA(cudaEventRecord(p->ev[0], ctx->stream));
-        const double zeroB[3] = {0.0, 0.0, 0.0};   // inversion.py:223 passes magneticField * 0 for gravity
-        PCUDA(launch_a_sens(GB_SENS_GRAV, zeroB, l.p, p->Ns, e.p, p->n, d->grav_mul, d->grav_div, p->A[0], p->lda, ctx->sm_count, ctx->stream));
-        PCUDA(launch_a_sens(GB_SENS_MAGN, d->magnetic_field, l.p, p->Ns, e.p, p->n, d->magn_mul, d->magn_div, p->A[1], p->lda, ctx->sm_count, ctx->stream));
+        if (!p->lean) {
+            PCUDA(sens_generate(p, 0, (int)yN, p->A[0], p->A[1], p->lda));
+        } else {
+            for (int64_t y0 = 0; y0 < yN; y0 += p->chunk_y)      // one full generation pass (timed: what every later fp64 pass costs)
+                PCUDA(sens_generate(p, (int)y0, (int)std::min<int64_t>(yN, y0 + p->chunk_y), p->Achunk[0], p->Achunk[1], p->chunk_ld));
+        }
         PCUDA(cudaEventRecord(p->ev[1], ctx->stream));
         PCUDA(cudaStreamSynchronize(ctx->stream));
         float t = 0.f;
@@ -645,6 +713,10 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
     const FftGeom fg = fft_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1);
     const KronGeom kg = kron_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1);
     const StencilGeom sg = stencil_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1, p->vox, h->gp_length);
+    if (p->lean && (h->slices == 0 || structured))
+        return gb_fail(ctx, GB_ERR_UNSUPPORTED, "this problem keeps no resident fp64 sensitivities (lean mode, %lld x %lld): only the dense int8 "
+                       "tensor-core path (slices = 4, 5, 6; structure = dense) runs on it; set GEOBO_B200_LEAN_A=0 if the matrices fit",
+                       (long long)p->Ns, (long long)p->N);
     if (compact && h->kernel_id != GB_KERNEL_SPARSE)
         return gb_fail(ctx, GB_ERR_UNSUPPORTED, "structure = compact needs kernelfunc 'sparse': only the compact-support kernels (kernels.py:101-138) "
                        "vanish outside a window of the voxel grid; use structure = dense");
@@ -696,7 +768,29 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
                 if (p->a8[c]) { gb_dev_free(ctx, p->a8[c]); p->a8[c] = nullptr; }
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a8[c], (size_t)ozaki_rows_bytes(Ns, p->Kp, S, ozaki_tile_np(S))));
                 if (!p->a_exp[c]) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a_exp[c], (size_t)Ns * sizeof(int)));
-                GB_CUDA(ctx, ozaki_slice_sens(p->A[c], Ns, p->N, p->lda, S, p->a_exp[c], p->a8[c], p->Kp, s));
+                if (!p->lean) GB_CUDA(ctx, ozaki_slice_sens(p->A[c], Ns, p->N, p->lda, S, p->a_exp[c], p->a8[c], p->Kp, s));
+            }
+            if (p->lean) {
+                // two generation passes: running row maxima -> exponents, then the digits of every chunk into its k steps
+                GB_CUDA(ctx, cudaMemsetAsync(p->a_amax, 0, (size_t)2 * Ns * sizeof(double), s));
+                GB_TRY(lean_for_each_chunk(p, [&](int64_t, int64_t ncols) -> cudaError_t {
+                    for (int c = 0; c < 2; ++c) {
+                        cudaError_t e = ozaki_row_absmax_accum(p->Achunk[c], Ns, ncols, p->chunk_ld, p->a_amax + c * Ns, s);
+                        if (e != cudaSuccess) return e;
+                    }
+                    return cudaSuccess;
+                }));
+                for (int c = 0; c < 2; ++c) {
+                    GB_CUDA(ctx, ozaki_exps_from_absmax(p->a_amax + c * Ns, Ns, p->a_exp[c], s));
+                    GB_CUDA(ctx, cudaMemsetAsync(p->a8[c], 0, (size_t)ozaki_rows_bytes(Ns, p->Kp, S, ozaki_tile_np(S)), s));
+                }
+                GB_TRY(lean_for_each_chunk(p, [&](int64_t j0, int64_t ncols) -> cudaError_t {
+                    for (int c = 0; c < 2; ++c) {
+                        cudaError_t e = ozaki_slice_rows_range(p->Achunk[c], Ns, ncols, p->chunk_ld, S, p->a_exp[c], p->a8[c], p->Kp, ozaki_tile_np(S), j0 / 32, s);
+                        if (e != cudaSuccess) return e;
+                    }
+                    return cudaSuccess;
+                }));
             }
             if (p->t8) { gb_dev_free(ctx, p->t8); p->t8 = nullptr; }
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->t8, (size_t)ozaki_table_bytes(p->ext, S)));
@@ -864,7 +958,14 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         double* rtmp = p->rf_t + 2 * Mp;
         const int nref = h->refine < 0 ? 0 : h->refine;
         for (int itr = 0; itr <= nref; ++itr) {
-            GB_CUDA(ctx, refine_at_alpha(ra, p->alpha, p->rf_w, s));       // w = A3^T alpha
+            if (!p->lean) {
+                GB_CUDA(ctx, refine_at_alpha(ra, p->alpha, p->rf_w, s));   // w = A3^T alpha
+            } else {
+                GB_TRY(lean_for_each_chunk(p, [&](int64_t j0, int64_t ncols) -> cudaError_t {
+                    return refine_at_alpha_chunk(ra, p->Achunk[0], p->Achunk[1], p->chunk_ld, j0, ncols, p->alpha, s);
+                }));
+                GB_CUDA(ctx, refine_at_alpha_finish(ra, p->alpha, p->rf_w, s));
+            }
             if (structured) {                                              // z = K w   (this rank's voxel columns)
                 for (int c = 0; c < nrp; ++c)                              // fixed order c = 0, 1, 2: deterministic sums (c = 2: zero weights without drill data)
                     GB_CUDA(ctx, apply_structured(c * 3, p->rf_w + (long)c * p->Kp, p->Kp, 1, p->rf_z, 0, c > 0));
@@ -874,7 +975,19 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
                 p->nlaunch += 3 + (refine_kw_slices(ncol) > 1 ? 1 : 0) + (p->nd ? 1 : 0);
             }
             if (itr == nref) break;                                        // z = K A3^T alpha = posterior mean
-            GB_CUDA(ctx, refine_a_z(ra, p->rf_z, rt, s));                  // t = A3 z  (partial over this rank's columns)
+            if (!p->lean) {
+                GB_CUDA(ctx, refine_a_z(ra, p->rf_z, rt, s));              // t = A3 z  (partial over this rank's columns)
+            } else {
+                bool first = true;
+                GB_TRY(lean_for_each_chunk(p, [&](int64_t j0, int64_t ncols) -> cudaError_t {
+                    const int64_t ja = std::max<int64_t>(j0, p->c0), jb = std::min<int64_t>(j0 + ncols, p->c1);
+                    if (jb <= ja) return cudaSuccess;
+                    cudaError_t e = refine_a_z_chunk(ra, p->Achunk[0], p->Achunk[1], p->chunk_ld, j0, ja, jb, p->rf_z, rt, first ? 0 : 1, s);
+                    first = false;
+                    return e;
+                }));
+                GB_CUDA(ctx, refine_a_z_drill(ra, p->rf_z, rt, s));
+            }
             GB_TRY(comm_allreduce_sum_f64(ctx, rt, (size_t)Mp));
             GB_CUDA(ctx, refine_residual(p->ydev, rt, p->alpha, Ns, M, Mp, h->gp_sigma, rr, s));
             GB_CUDA(ctx, refine_apply_inverse(p->Linv, Mp, rr, rtmp, p->alpha, 1, s));   // alpha += L^-T L^-1 r
@@ -976,10 +1089,31 @@ extern "C" int gb_neg_logl(gb_problem* p, const gb_hyper* h, double* neg_logl, i
     return GB_OK;
 }
 
+// y (+)= A[:, j0 : j0 + ncols) x[j0 : j0 + ncols)   (one warp per row; lean mode of gb_forward)
+__global__ void gemv_chunk_kernel(const double* __restrict__ A, long rows, long cols, long ld, const double* __restrict__ x,
+                                  double* __restrict__ y, int accumulate) {
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (long c = lane; c < cols; c += 32) acc = fma(A[row * ld + c], x[c], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[row] = accumulate ? y[row] + acc : acc;
+}
+
 extern "C" int gb_problem_get_sens(gb_problem* p, int kind, double* out) {
     if (!p || !out || (kind != GB_SENS_GRAV && kind != GB_SENS_MAGN)) return GB_ERR_ARG;
     gb_ctx* ctx = p->ctx;
     GB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (p->lean) {
+        GB_TRY(lean_for_each_chunk(p, [&](int64_t j0, int64_t ncols) -> cudaError_t {
+            cudaError_t e = cudaMemcpy2DAsync(out + j0, p->N * sizeof(double), p->Achunk[kind], p->chunk_ld * sizeof(double), ncols * sizeof(double),
+                                              p->Ns, cudaMemcpyDeviceToHost, ctx->stream);
+            return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
+        }));
+        return GB_OK;
+    }
     GB_CUDA(ctx, cudaMemcpy2DAsync(out, p->N * sizeof(double), p->A[kind], p->lda * sizeof(double), p->N * sizeof(double), p->Ns,
                                    cudaMemcpyDeviceToHost, ctx->stream));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -994,7 +1128,14 @@ extern "C" int gb_forward(gb_problem* p, int kind, const double* x, double* out)
     GB_CUDA(ctx, xd.alloc(p->N));
     GB_CUDA(ctx, yd.alloc(p->Ns));
     GB_CUDA(ctx, cudaMemcpyAsync(xd.p, x, p->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    GB_CUDA(ctx, launch_gemv(p->A[kind], p->Ns, p->N, p->lda, xd.p, yd.p, ctx->stream));
+    if (p->lean) {
+        GB_TRY(lean_for_each_chunk(p, [&](int64_t j0, int64_t ncols) -> cudaError_t {
+            gemv_chunk_kernel<<<(unsigned)((p->Ns + 7) / 8), 256, 0, ctx->stream>>>(p->Achunk[kind], p->Ns, ncols, p->chunk_ld, xd.p + j0, yd.p, j0 > 0);
+            return cudaGetLastError();
+        }));
+    } else {
+        GB_CUDA(ctx, launch_gemv(p->A[kind], p->Ns, p->N, p->lda, xd.p, yd.p, ctx->stream));
+    }
     GB_CUDA(ctx, cudaMemcpyAsync(out, yd.p, p->Ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GB_OK;

@@ -48,15 +48,33 @@ __global__ void row_absmax_kernel(const double* __restrict__ A, long rows, long 
     if (lane == 0) exps[row] = scale_exp(m);
 }
 
+// running row maxima over column chunks of an operand that is never resident as a whole
+__global__ void row_absmax_accum_kernel(const double* __restrict__ A, long rows, long cols, long ld, double* __restrict__ amax) {
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    double m = 0.0;
+    for (long c = lane; c < cols; c += 32) m = fmax(m, fabs(A[row * ld + c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) amax[row] = fmax(amax[row], m);
+}
+
+__global__ void exps_from_absmax_kernel(const double* __restrict__ amax, long rows, int* __restrict__ exps) {
+    const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < rows) exps[row] = scale_exp(amax[row]);
+}
+
 // A (rows x ld fp64, cols valid) -> pre-tiled digit blocks [row tile of TR rows][k step][digit][TR x 32 B canonical layout];
 // one thread per (row, 16 consecutive contraction indices): S 16-byte stores.  Rows >= rows and columns >= cols are zero.
 // TR = 128 for an M-side (A) operand, TR = NT for an N-side (B) operand.
 template <int S>
 __global__ void slice_rows_tiled_kernel(const double* __restrict__ A, long rows, long cols, long ld, const int* __restrict__ exps,
-                                        uint8_t* __restrict__ out, long ksteps, int TR) {
-    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;    // 16-column group
+                                        uint8_t* __restrict__ out, long ksteps, int TR, long ks0, long ks_count) {
+    // ksteps: k steps of the whole layout; this launch fills steps [ks0, ks0 + ks_count) from the columns of A (a column chunk)
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;    // 16-column group of the chunk
     const long row = blockIdx.y;
-    if (g >= 2 * ksteps) return;
+    if (g >= 2 * ks_count) return;
     uint32_t pk[S][4];
 #pragma unroll
     for (int q = 0; q < S; ++q) pk[q][0] = pk[q][1] = pk[q][2] = pk[q][3] = 0u;
@@ -73,7 +91,7 @@ __global__ void slice_rows_tiled_kernel(const double* __restrict__ A, long rows,
             }
         }
     }
-    const long tile = row / TR, ks = g >> 1;
+    const long tile = row / TR, ks = ks0 + (g >> 1);
     const long blk = (long)TR * 32;
     const uint32_t off = core_offset((uint32_t)(row % TR), (uint32_t)(g & 1));
 #pragma unroll
@@ -411,9 +429,34 @@ cudaError_t ozaki_slice_rows(const double* A, long rows, long cols, long ld, int
     const long ksteps = kp / 32, rows_p = (rows + tr - 1) / tr * tr;
     dim3 grid((unsigned)((2 * ksteps + 127) / 128), (unsigned)rows_p);
     switch (slices) {
-        case 4: ozaki::slice_rows_tiled_kernel<4><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr); break;
-        case 5: ozaki::slice_rows_tiled_kernel<5><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr); break;
-        case 6: ozaki::slice_rows_tiled_kernel<6><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr); break;
+        case 4: ozaki::slice_rows_tiled_kernel<4><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr, 0, ksteps); break;
+        case 5: ozaki::slice_rows_tiled_kernel<5><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr, 0, ksteps); break;
+        case 6: ozaki::slice_rows_tiled_kernel<6><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr, 0, ksteps); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t ozaki_row_absmax_accum(const double* A, long rows, long cols, long ld, double* amax, cudaStream_t s) {
+    ozaki::row_absmax_accum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(A, rows, cols, ld, amax);
+    return cudaGetLastError();
+}
+
+cudaError_t ozaki_exps_from_absmax(const double* amax, long rows, int* exps, cudaStream_t s) {
+    ozaki::exps_from_absmax_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(amax, rows, exps);
+    return cudaGetLastError();
+}
+
+// digits of a column chunk (cols columns of A, ld) into k steps [ks0, ks0 + ceil(cols / 32)) of a layout with kp_total / 32 steps
+cudaError_t ozaki_slice_rows_range(const double* A, long rows, long cols, long ld, int slices, const int* exps, uint8_t* out, long kp_total,
+                                   int tr, long ks0, cudaStream_t s) {
+    const long ksteps = kp_total / 32, ks_count = (cols + 31) / 32, rows_p = (rows + tr - 1) / tr * tr;
+    if (ks0 < 0 || ks0 + ks_count > ksteps) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)((2 * ks_count + 127) / 128), (unsigned)rows_p);
+    switch (slices) {
+        case 4: ozaki::slice_rows_tiled_kernel<4><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr, ks0, ks_count); break;
+        case 5: ozaki::slice_rows_tiled_kernel<5><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr, ks0, ks_count); break;
+        case 6: ozaki::slice_rows_tiled_kernel<6><<<grid, 128, 0, s>>>(A, rows, cols, ld, exps, out, ksteps, tr, ks0, ks_count); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

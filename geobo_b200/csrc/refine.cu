@@ -149,12 +149,14 @@ __global__ void __launch_bounds__(256) kw_kernel(const double* __restrict__ tabl
 
 // t[c*Ns + s] = sum_{j < ncol} A_c[s][c0 + j] z[c][j]   (warp per row)
 __global__ void __launch_bounds__(256) a_gemv_kernel(const double* __restrict__ A0, const double* __restrict__ A1, long Ns, long lda, long c0,
-                                                     long ncol, const double* __restrict__ z, long ncp, double* __restrict__ t) {
+                                                     long ncol, const double* __restrict__ z, long ncp, double* __restrict__ t,
+                                                     long zoff, int accumulate) {
+    // c0: first column inside A's rows, zoff: first entry of z[c] (they differ when A is a column chunk of the matrix)
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31, c = blockIdx.y;
     if (row >= Ns) return;
     const double* a = (c ? A1 : A0) + row * lda + c0;
-    const double* zc = z + (long)c * ncp;
+    const double* zc = z + (long)c * ncp + zoff;
     double s0 = 0.0, s1 = 0.0;
     long j = lane;
     for (; j + 32 < ncol; j += 64) {
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(256) a_gemv_kernel(const double* __restrict__ 
     double s = s0 + s1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) t[c * Ns + row] = s;
+    if (lane == 0) t[c * Ns + row] = accumulate ? t[c * Ns + row] + s : s;
 }
 
 // drill rows of A3 z: z[2][drill - c0] when the drilled voxel is in this rank's shard, else 0 (other ranks add it)
@@ -280,8 +282,33 @@ cudaError_t refine_kw(const RefineArgs& a, const double* w, double* z, cudaStrea
 
 cudaError_t refine_a_z(const RefineArgs& a, const double* z, double* t, cudaStream_t s) {
     dim3 grid((unsigned)((a.Ns + 7) / 8), 2);
-    a_gemv_kernel<<<grid, 256, 0, s>>>(a.A[0], a.A[1], a.Ns, a.lda, a.c0, a.ncol, z, a.ncp, t);
+    a_gemv_kernel<<<grid, 256, 0, s>>>(a.A[0], a.A[1], a.Ns, a.lda, a.c0, a.ncol, z, a.ncp, t, 0, 0);
+    return refine_a_z_drill(a, z, t, s);
+}
+
+cudaError_t refine_a_z_drill(const RefineArgs& a, const double* z, double* t, cudaStream_t s) {
     if (a.nd) t_drill_kernel<<<(unsigned)((a.nd + 255) / 256), 256, 0, s>>>(z + 2 * a.ncp, a.drill, a.nd, a.c0, a.c0 + a.ncol, t + 2 * a.Ns);
+    return cudaGetLastError();
+}
+
+cudaError_t refine_a_z_chunk(const RefineArgs& a, const double* A0, const double* A1, long ld, long j0, long ja, long jb, const double* z,
+                             double* t, int accumulate, cudaStream_t s) {
+    if (jb <= ja) return cudaSuccess;
+    dim3 grid((unsigned)((a.Ns + 7) / 8), 2);
+    a_gemv_kernel<<<grid, 256, 0, s>>>(A0, A1, a.Ns, ld, ja - j0, jb - ja, z, a.ncp, t, ja - a.c0, accumulate);
+    return cudaGetLastError();
+}
+
+cudaError_t refine_at_alpha_chunk(const RefineArgs& a, const double* A0, const double* A1, long ld, long j0, long ncols, const double* alpha,
+                                  cudaStream_t s) {
+    dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)a.nsplit, 2);
+    at_gemv_partial_kernel<<<grid, 256, 0, s>>>(A0, A1, a.Ns, ncols, ld, alpha, a.nsplit, a.partial + j0, a.Kp);
+    return cudaGetLastError();
+}
+
+cudaError_t refine_at_alpha_finish(const RefineArgs& a, const double* alpha, double* w, cudaStream_t s) {
+    w_reduce_kernel<<<(unsigned)((a.Kp + 255) / 256), 256, 0, s>>>(a.partial, a.nsplit, a.Kp, a.N, w);
+    if (a.nd) w_drill_kernel<<<(unsigned)((a.nd + 255) / 256), 256, 0, s>>>(alpha + 2 * a.Ns, a.drill, a.nd, w + 2 * a.Kp);
     return cudaGetLastError();
 }
 

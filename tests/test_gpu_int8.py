@@ -82,6 +82,39 @@ def test_precision_auto_default_uses_the_tensor_core_path_where_admissible(ctx, 
         assert normwise_err(a, r) < 1e-7, n
 
 
+@pytest.mark.parametrize("shape,kf,nd", [((5, 6, 16), "exp", 3), ((9, 5, 16), "sparse", 0), ((6, 5, 32), "matern32", 5)])
+def test_lean_mode_regenerated_sensitivities_match_resident_ones(ctx, monkeypatch, shape, kf, nd):
+    """GEOBO_B200_LEAN_A=1: no resident fp64 sensitivities -- digit extraction, A3^T alpha, A3 z and gb_forward regenerate them in
+    column chunks (two voxel rows per chunk here: several chunks, a ragged last one for odd yNcube).  Same digits, same
+    exponents; only the summation order of the two refinement GEMVs changes."""
+    from geobo_b200 import _lib
+    c = configure(base_cfg(), xNcube=shape[0], yNcube=shape[1], zNcube=shape[2], kernelfunc=kf, precision="int8x5")
+    f = synthetic_inputs(c, nd)
+    gl = c.gp_lengthscale * c.xvoxsize * (np.array([1.0, 1.01, 1.02]) if kf == "matern32" else np.ones(3))
+    inv0, out0 = run_cubing(f, gl=gl.copy())
+    A0 = inv0._problem.sens("magn")
+    x = np.random.default_rng(0).standard_normal(A0.shape[1])
+    fw0 = inv0._problem.forward("grav", x)
+    monkeypatch.setenv("GEOBO_B200_LEAN_A", "1")
+    monkeypatch.setenv("GEOBO_B200_LEAN_CHUNK_ROWS", "2")
+    inv1, out1 = run_cubing(f, gl=gl.copy())
+    assert np.array_equal(inv1._problem.sens("magn"), A0)
+    fw1 = inv1._problem.forward("grav", x)
+    assert np.abs(fw1 - fw0).max() <= 1e-12 * np.abs(fw0).max()
+    for n, a, b in zip(CUBES, out1, out0):
+        assert normwise_err(a, b) < 1e-11, n
+    assert abs(inv1.logl - inv0.logl) < 1e-10 * abs(inv0.logl)
+    with np.errstate(all="ignore"):
+        ref, ex = o.cubing_lean(c, f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"], gp_length=gl.copy())
+    for n, a, r in zip(CUBES, out1, ref):
+        assert normwise_err(a, r) < 1e-6, n
+    # the fp64 path and the structured projections need resident rows: refused loudly on a lean problem
+    configure(base_cfg(), xNcube=shape[0], yNcube=shape[1], zNcube=shape[2], kernelfunc=kf, precision="fp64")
+    with pytest.raises(_lib.GeoboB200Error) as e:
+        run_cubing(f, gl=gl.copy())
+    assert "lean" in str(e.value)
+
+
 def test_int8_full_size_32cube_vs_fp64_path(ctx):
     """BASELINE config 2 size (N = 32768, M = 2048, exp kernel, cond ~ 1e6): slice path against the fp64 DMMA path
     on the same device problem, plus linearity of the mean in the data."""

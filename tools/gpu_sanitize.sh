@@ -9,7 +9,7 @@ for T in $TOOLS; do
   EXTRA=""
   [ "$T" = "memcheck" ] && EXTRA="--leak-check full"
   [ "$T" = "racecheck" ] && EXTRA="--racecheck-report all"
-  timeout 1500 compute-sanitizer --tool $T $EXTRA --error-exitcode 9 --print-limit 40 \
+  timeout 600 compute-sanitizer --tool $T $EXTRA --error-exitcode 9 --print-limit 40 \
       python tools/sanitize_cases.py > gpurun_out/sanitize_${T}_${TAG}.log 2>&1
   echo "sanitize $T rc=$?"; grep -c SANITIZE_CASE_OK gpurun_out/sanitize_${T}_${TAG}.log; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|LEAK SUMMARY" gpurun_out/sanitize_${T}_${TAG}.log | tail -3
 done
