@@ -17,7 +17,8 @@ KERNEL_IDS = {"sparse": 0, "exp": 1, "matern32": 2}
 STRUCTURE_IDS = {"dense": 0, "kron": 1, "compact": 2, "fft": 3}     # gb_hyper.structure (GB_STRUCTURE_*)
 SENS_KINDS = {"grav": 0, "magn": 1}
 FLAG_MEAN, FLAG_VAR, FLAG_LOGL, FLAG_ALL = 1, 2, 4, 7
-TIMER_NAMES = ["a_sens", "tables", "project", "drill_rows", "aka", "allreduce", "chol", "trsm", "mean_var", "total", "d2h", "launches"]
+TIMER_NAMES = ["a_sens", "tables", "project", "drill_rows", "aka", "allreduce", "chol", "trsm", "mean_var", "total", "d2h", "launches",
+               "ksteps_frac"]
 
 
 class GeoboB200Error(RuntimeError):

@@ -347,6 +347,9 @@ struct gb_problem {
     int* a_exp[2] = {nullptr, nullptr};
     uint8_t* t8 = nullptr;
     int* t_exp = nullptr;
+    unsigned int* sync_ctr = nullptr;    // [4] words: [0] arrival counter of the projection kernel's tile rounds, [2..3] K steps visited (u64)
+    double ksteps_total = 0.0;           // K steps of the last projection launch without culling (tiles x steps)
+    int* cull_ext = nullptr;             // [9][2] extents of the non-zero table digits (zero-digit culling of the projection's K steps)
     int a8_slices = 0;
     // int8 variance path: explicit Linv, its digit blocks, transposed digit blocks of Pt, per-row-tile column sums of squares
     double* Linv = nullptr;              // [Mp][Mp]
@@ -402,7 +405,7 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
-                    p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp,
+                    p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp, p->cull_ext, p->sync_ctr,
                     p->Linv, p->tmpL, p->alpha, p->l8, p->l_exp, p->b8, p->b_exp, p->partial,
                     p->edges_dev, p->loc_dev, p->Achunk[0], p->Achunk[1], p->a_amax,
                     p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch, p->chol_stage, p->chol_pan, p->chol_paninfo, p->kron_f, p->kron_T, p->fft_W, p->fft_tw, p->fft_scratch,
@@ -676,6 +679,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
     if (nrp > p->cap_nrp) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "all three property blocks requested on a problem sized for two");
     p->nrp = nrp;
     p->ldp = (int64_t)nrp * p->ncp;
+    p->ksteps_total = 0.0;
     p->last_full = full;
     p->nlaunch = 0;
     CovParams cp;
@@ -795,6 +799,8 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             if (p->t8) { gb_dev_free(ctx, p->t8); p->t8 = nullptr; }
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->t8, (size_t)ozaki_table_bytes(p->ext, S)));
             if (!p->t_exp) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->t_exp, 16 * sizeof(int)));
+            if (!p->cull_ext) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->cull_ext, 18 * sizeof(int)));
+            if (!p->sync_ctr) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->sync_ctr, 4 * sizeof(unsigned int)));
             // digit scratch shared by the AkA products (row digits of three Pt blocks) and the variance product
             // (transposed digits of all of Pt): the two uses are sequential
             if (p->b8) { gb_dev_free(ctx, p->b8); p->b8 = nullptr; }
@@ -821,6 +827,27 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         oa.t8 = p->t8; oa.t_exp = p->t_exp; oa.L = p->L; oa.Pt = p->Pt;
         oa.ext = p->ext; oa.C0 = p->C0; oa.kp = p->Kp; oa.ldp = ldp; oa.ncp = ncp;
         oa.Ns = (int)Ns; oa.ncol = (int)ncol; oa.c0 = (int)p->c0; oa.nr = nrp;
+        // zero-digit culling (bitwise-neutral, default on; GEOBO_B200_CULL=0 visits every K step)
+        bool cull = true;
+        if (const char* ev = getenv("GEOBO_B200_CULL")) cull = atoi(ev) != 0;
+        oa.cull = nullptr;
+        if (cull) {
+            GB_CUDA(ctx, ozaki_table_extents(p->t8, p->ext, S, p->n, p->cull_ext, s));
+            oa.cull = p->cull_ext;
+            p->nlaunch += 1;
+        }
+        oa.n[0] = (int)p->n[0]; oa.n[1] = (int)p->n[1]; oa.n[2] = (int)p->n[2];
+        // tile-round pacing (default on; GEOBO_B200_TILE_SYNC=0: free-running CTAs)
+        bool pace = true;
+        if (const char* ev = getenv("GEOBO_B200_TILE_SYNC")) pace = atoi(ev) != 0;
+        oa.sync_ctr = nullptr;
+        GB_CUDA(ctx, cudaMemsetAsync(p->sync_ctr, 0, 4 * sizeof(unsigned int), s));
+        if (pace) oa.sync_ctr = p->sync_ctr;
+        oa.steps_ctr = reinterpret_cast<unsigned long long*>(p->sync_ctr + 2);
+        {
+            const int nt_ = ozaki_tile_np(S);
+            p->ksteps_total = 2.0 * nrp * (double)((Ns + nt_ - 1) / nt_) * (double)((ncol + 127) / 128) * (double)(p->Kp / 32);
+        }
         GB_CUDA(ctx, ozaki_project(oa, S, ctx->sm_count, s));
         p->nlaunch += 2;                  // table slicing (absmax + digits)
     } else {
@@ -1027,6 +1054,12 @@ static int collect_timings(gb_problem* p) {
     float t = 0.f;
     GB_CUDA(ctx, cudaEventElapsedTime(&t, p->ev[0], p->ev[8]));
     p->ms[GB_T_TOTAL] = t;
+    p->ms[GB_T_KSTEPS] = 1.0;
+    if (p->sync_ctr && p->ksteps_total > 0.0) {      // the stream is idle here (the callers synchronise before collecting)
+        unsigned long long done = 0;
+        GB_CUDA(ctx, cudaMemcpy(&done, p->sync_ctr + 2, sizeof done, cudaMemcpyDeviceToHost));
+        if (done > 0) p->ms[GB_T_KSTEPS] = (double)done / p->ksteps_total;
+    }
     {
         // kernels launched by run_predict: set_y, tables, projection (+ digit slicing), [drill rows x2], aka, noise diag,
         // Cholesky (potrf + panel + trailing per block), u solve (2 GEMMs per block), dot; the mean / variance

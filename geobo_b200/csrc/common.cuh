@@ -140,7 +140,13 @@ struct OzakiArgs {
     long ext, C0, kp, ldp, ncp;
     int Ns, ncol, c0;
     int nr;                  // property blocks computed per data block: 3, or 2 when there is no drill data (block 2 is NaN in the reference)
+    const int* cull;         // [9][2] device: extents (|dy|, |dx|) of the non-zero digits of every table (ozaki_table_extents), or null
+    int n[3];                // xN, yN, zN
+    unsigned long long* steps_ctr;   // device counter, ZERO at launch: K steps visited (sum over tiles); or null
+    unsigned int* sync_ctr;  // device counter, ZERO at launch: tile-round pacing of the copy lanes (keeps the shared K strips in L2); or null
 };
+// cull[2 tb + 0 / 1] = largest |dy| / |dx| lattice offset with a non-zero digit in any plane of table tb (after ozaki_slice_tables)
+cudaError_t ozaki_table_extents(const uint8_t* t8, long ext, int slices, const int64_t n[3], int* cull /*[18]*/, cudaStream_t s);
 int ozaki_tile_n(int slices);
 int ozaki_tile_np(int slices);
 int ozaki_chunk();

@@ -141,8 +141,72 @@ struct Params {
     long ext, C0, kp, ldp, ncp;
     int Ns, ncol, c0, chunk;  // chunk: contraction indices per accumulator flush (multiple of 32)
     int nr;                   // property blocks per data block (3, or 2 without drill data): task t = (c = t / nr, r = t % nr)
+    // zero-digit culling: cull[2 * task + 0 / 1] = largest |dy| / |dx| lattice offset at which ANY digit plane of the task's
+    // covariance table is non-zero (device memory, written by table_extent_kernel); null = visit every K step
+    const int* cull;
+    int xN, yN, zN;
+    // tile-round pacing: the CTAs take tiles round-robin, and the (up to) gridDim.x tiles of one round share ONE sensitivity-digit
+    // K strip (same sensor-row tile), which therefore only has to come from HBM once -- as long as the CTAs stay within an
+    // L2-full of each other.  Left alone they drift apart (measured at 64x64x32: 3.98 TB read from HBM for a 5.4 GB operand), so
+    // the copy lanes count arrivals in this device counter and start a round's loads together.  null = no pacing.
+    unsigned int* sync_ctr;
+    unsigned long long* steps_ctr;   // += K steps visited (one add per tile), for the roofline accounting; or null
     int n_stile, n_itile;     // sensor-row tiles of NT, voxel-column tiles of 128
 };
+
+// K steps a tile has to visit.  Beyond the offsets (ey, ex) every digit of the task's covariance table is zero (a kernel with
+// compact support, or one that decays below the last digit: exp(-d^2 / 2 gamma^2) < 2^-39 beyond 7.3 gamma), so a K step whose
+// 32 contraction voxels all lie further than that from all 128 output voxels of the tile multiplies by zero digits only: skipping
+// it leaves every integer accumulator -- and the result -- bitwise unchanged.  The contraction index is y-major, so the kept steps
+// are `nrows` voxel rows jy >= jya with the same window of `w` steps at offset `koff` inside each row (rowsteps = xN zN / 32 per
+// row):  ks(t) = (jya + t / w) * rowsteps + koff + t % w,  t = 0 .. nt - 1.  Without culling: one "row" of all ksteps steps.
+struct KRange {
+    int jya, nrows, koff, w, rowsteps;
+    uint32_t nt;
+    __device__ __forceinline__ int ks(uint32_t t) const { const uint32_t jj = t / (uint32_t)w; return (jya + (int)jj) * rowsteps + koff + (int)(t - jj * (uint32_t)w); }
+};
+
+__device__ __forceinline__ KRange tile_krange(const Params& P, int task, int itile, int ksteps) {
+    KRange r;
+    const int XZ = P.xN * P.zN;
+    if (P.cull == nullptr || (XZ & 31) != 0) {
+        r.jya = 0; r.nrows = 1; r.koff = 0; r.w = ksteps; r.rowsteps = 0; r.nt = (uint32_t)ksteps;
+        return r;
+    }
+    const int ey = P.cull[2 * task], ex = P.cull[2 * task + 1];
+    const long g0 = (long)P.c0 + (long)itile * 128;
+    const long g1 = min(g0 + 127, (long)P.c0 + P.ncol - 1);
+    const int iya = (int)(g0 / XZ), iyb = (int)(g1 / XZ);
+    int ixa = 0, ixb = P.xN - 1;
+    if (iya == iyb) { ixa = (int)(g0 % XZ) / P.zN; ixb = (int)(g1 % XZ) / P.zN; }
+    const int jya = max(0, iya - ey), jyb = min(P.yN - 1, iyb + ey);
+    const int jxa = max(0, ixa - ex), jxb = min(P.xN - 1, ixb + ex);
+    r.rowsteps = XZ / 32;
+    r.jya = jya;
+    r.nrows = jyb - jya + 1;
+    r.koff = (jxa * P.zN) / 32;
+    r.w = ((jxb + 1) * P.zN + 31) / 32 - r.koff;
+    r.nt = (uint32_t)(r.nrows * r.w);
+    return r;
+}
+
+// extents of the non-zero digits of the 9 covariance tables: out[2 tb + 0 / 1] = max |dy| / |dx| with a non-zero digit in any plane
+template <int S>
+__global__ void table_extent_kernel(const uint8_t* __restrict__ t8, long ext, int xN, int yN, int zN, int* __restrict__ out) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tb = blockIdx.y;
+    if (e >= ext) return;
+    const long plane = plane_stride(ext);
+    bool nz = false;
+#pragma unroll
+    for (int q = 0; q < S; ++q) nz |= t8[((long)tb * S + q) * plane + e] != 0;
+    if (!nz) return;
+    const int EX = 2 * xN - 1, EZ = 2 * zN - 1;
+    const long t = e / EZ;
+    const int dx = (int)(t % EX) - (xN - 1), dy = (int)(t / EX) - (yN - 1);
+    atomicMax(out + 2 * tb, abs(dy));
+    atomicMax(out + 2 * tb + 1, abs(dx));
+}
 
 constexpr int PROD_SLOTS = 3;                          // producer warps per TMEM lane quarter
 constexpr int TS_THREADS = (6 + 4 * PROD_SLOTS) * 32;  // 4 epilogue + MMA + copy + 12 producer warps
@@ -198,10 +262,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
         const long plane = plane_stride(P.ext);
         const int C0 = (int)P.C0;
         uint32_t it_tile0 = 0;
-        for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it_tile0 += (uint32_t)ksteps) {
+        for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int tq = (int)(tile / tiles_per_task);
             const int task = (tq / P.nr) * 3 + tq % P.nr;             // c * 3 + r
             const int itile = (int)((tile % tiles_per_task) % P.n_itile);
+            const KRange kr = tile_krange(P, task, itile, ksteps);
+            const int nt = (int)kr.nt;
             const int i0 = itile * 128 + 32 * q4 + (lane & 16);       // first voxel column of this half-warp's segment
             const uint8_t* t8 = P.t8 + (size_t)task * S * plane;
             const int lseg = P.L[P.c0 + min(i0, P.ncol - 16)];
@@ -213,8 +279,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
             uint32_t word[2][S];                           // table words of step ks
             int wi[2];
             uint32_t sh[2];
-            auto load_lj = [&](int k, int (&lj)[2]) {
-                const int kk = min(k, ksteps - 1);
+            auto load_lj = [&](int k, int (&lj)[2]) {          // k: step index t of this tile
+                const int kk = kr.ks((uint32_t)min(k, nt - 1));
                 lj[0] = P.L[kk * 32];
                 lj[1] = P.L[kk * 32 + 16];
             };
@@ -236,7 +302,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
                 load_lj(ks + PROD_SLOTS, lj_nn);
                 load_words(lj0);
             }
-            for (; ks < ksteps; ks += PROD_SLOTS) {
+            for (; ks < nt; ks += PROD_SLOTS) {                // ks: step index t of this tile (kr.ks(t) = K step)
                 const uint32_t it = it_tile0 + (uint32_t)ks;
                 // ---- assemble the unaligned 16-byte windows of this step: v[q][0..3] = K half 0, v[q][4..7] = K half 1
                 uint32_t v[S][8];
@@ -273,20 +339,34 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[it % SB]);
             }
+            it_tile0 += kr.nt;
         }
     } else if (warp == 5) {
         // =============================================================== sensitivity-digit copies (one elected lane)
         if (lane == 0) {
             uint32_t it = 0;
+            unsigned int target = 0;
             for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (P.sync_ctr) {
+                    // all CTAs are co-resident (grid <= SM count, one CTA per SM), so waiting on the others cannot deadlock
+                    const long first = tile - blockIdx.x;                                   // first tile of this round
+                    target += (unsigned int)min((long)gridDim.x, ntiles - first);           // arrivals up to and including this round
+                    atomicAdd(P.sync_ctr, 1u);
+                    while (*(volatile unsigned int*)P.sync_ctr < target) __nanosleep(256);
+                }
                 const int tq = (int)(tile / tiles_per_task);
                 const int stile = (int)((tile % tiles_per_task) / P.n_itile);
                 const uint8_t* src = P.a8[tq / P.nr] + (size_t)stile * ksteps * B_BYTES;
-                for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                    const int st = (int)(it % SB);
-                    mbar_wait(&done_bar[st], ((it / SB) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[st], B_BYTES);
-                    bulk_g2s(smem + st * B_BYTES, src + (size_t)ks * B_BYTES, B_BYTES, &full_bar[st]);
+                const KRange kr = tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, (int)((tile % tiles_per_task) % P.n_itile), ksteps);
+                if (P.steps_ctr) atomicAdd(P.steps_ctr, (unsigned long long)kr.nt);
+                for (int jj = 0; jj < kr.nrows; ++jj) {
+                    const uint8_t* rowsrc = src + (size_t)((kr.jya + jj) * kr.rowsteps + kr.koff) * B_BYTES;
+                    for (int q = 0; q < kr.w; ++q, ++it) {
+                        const int st = (int)(it % SB);
+                        mbar_wait(&done_bar[st], ((it / SB) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[st], B_BYTES);
+                        bulk_g2s(smem + st * B_BYTES, rowsrc + (size_t)q * B_BYTES, B_BYTES, &full_bar[st]);
+                    }
                 }
             }
         }
@@ -305,8 +385,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
             uint64_t* fb = full_bar;
             uint64_t* db = done_bar;
             for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int k0 = 0; k0 < ksteps; k0 += chunk_steps, ++chunk_id) {
-                    const int k1 = min(ksteps, k0 + chunk_steps);
+                const int tq = (int)(tile / tiles_per_task);
+                const int nt = (int)tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, (int)((tile % tiles_per_task) % P.n_itile), ksteps).nt;
+                for (int k0 = 0; k0 < nt; k0 += chunk_steps, ++chunk_id) {
+                    const int k1 = min(nt, k0 + chunk_steps);
                     mbar_wait(&tempty_bar, (chunk_id & 1) ^ 1);     // epilogue has drained the accumulators
                     tc_fence_after();
                     for (int ks = k0; ks < k1; ++ks) {
@@ -350,7 +432,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
             const int ebase = P.t_exp[task] - 14 - 8 * (S - 1);
             const int* aexp = P.a_exp[c];
             double* pcol = P.Pt + ((long)c * P.Ns + s0) * P.ldp + (long)r * P.ncp + (col_ok ? i : 0);
-            for (int k0 = 0; k0 < ksteps; k0 += chunk_steps, ++chunk_id) {
+            const int nt = (int)tile_krange(P, task, itile, ksteps).nt;
+            for (int k0 = 0; k0 < nt; k0 += chunk_steps, ++chunk_id) {
                 mbar_wait(&tfull_bar, chunk_id & 1);
                 tc_fence_after();
                 for (int n0 = 0; n0 < NT; n0 += 8) {
@@ -479,6 +562,19 @@ cudaError_t ozaki_slice_tables(const double* tables, long ext, int slices, int* 
     return cudaGetLastError();
 }
 
+cudaError_t ozaki_table_extents(const uint8_t* t8, long ext, int slices, const int64_t n[3], int* cull, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(cull, 0, 18 * sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((ext + 255) / 256), 9);
+    switch (slices) {
+        case 4: ozaki::table_extent_kernel<4><<<grid, 256, 0, s>>>(t8, ext, (int)n[0], (int)n[1], (int)n[2], cull); break;
+        case 5: ozaki::table_extent_kernel<5><<<grid, 256, 0, s>>>(t8, ext, (int)n[0], (int)n[1], (int)n[2], cull); break;
+        case 6: ozaki::table_extent_kernel<6><<<grid, 256, 0, s>>>(t8, ext, (int)n[0], (int)n[1], (int)n[2], cull); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 long ozaki_table_bytes(long ext, int slices) { return 9L * slices * ozaki::plane_stride(ext); }
 
 cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStream_t s) {
@@ -488,6 +584,10 @@ cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStre
     P.ext = a.ext; P.C0 = a.C0; P.kp = a.kp; P.ldp = a.ldp; P.ncp = a.ncp;
     P.Ns = a.Ns; P.ncol = a.ncol; P.c0 = a.c0;
     P.nr = a.nr == 2 ? 2 : 3;
+    P.cull = a.cull;
+    P.sync_ctr = a.sync_ctr;
+    P.steps_ctr = a.steps_ctr;
+    P.xN = a.n[0]; P.yN = a.n[1]; P.zN = a.n[2];
     P.chunk = ozaki_chunk();
     P.n_stile = 0;
     P.n_itile = 0;

@@ -68,6 +68,8 @@ extern "C" {
 #define GB_T_MEANVAR 8     /* fp64: mean + variance diag from V; int8: variance finalisation */
 #define GB_T_TOTAL 9       /* whole gb_predict on device          */
 #define GB_T_D2H 10        /* result copies to host               */
+#define GB_T_KSTEPS 12     /* int8 projection: fraction of the K steps (32 contraction voxels x one tile) actually visited; the others
+                              multiply by all-zero covariance digits and are skipped (a ratio, not ms; 1 = every step)  */
 #define GB_T_LAUNCHES 11   /* number of library kernels launched by the last gb_predict / gb_neg_logl (a count, not ms) */
 
 typedef struct gb_ctx gb_ctx;

@@ -142,7 +142,13 @@ def test_cubing_tiny_vs_live_reference_fixture(ctx, name):
         assert normwise_err(a, f[n]) < TOL_CUBE, n
     assert abs(inv.logl - float(f["logl"])) < 1e-7 * abs(float(f["logl"]))
     assert np.array_equal(inv.gp_length, f["gl_after"])          # Q1 mutation visible on the instance
-    assert normwise_err(inv.mu_rec, f["mu_rec"]) < TOL_CUBE
+    nvox = inv.mu_rec.size // 3
+    if f["Fs3"].size == 2 * 48:
+        # no drill data: the drill property is NaN in the reference's cubes (std of an empty array, Q9); the library does not
+        # compute that block at all, so mu_rec carries NaN there instead of the reference's (unused) finite numbers
+        assert normwise_err(inv.mu_rec[:2 * nvox], f["mu_rec"][:2 * nvox]) < TOL_CUBE and np.isnan(inv.mu_rec[2 * nvox:]).all()
+    else:
+        assert normwise_err(inv.mu_rec, f["mu_rec"]) < TOL_CUBE
     # dense attributes the reference keeps on the instance, materialised lazily
     M = f["Fs3"].size
     assert inv.Asens3.shape == (M, 3 * 240)
@@ -297,8 +303,9 @@ def test_full_size_properties_32cube(ctx):
     for y in (y1, y2, 2.0 * y1 - 0.5 * y2):
         prob.set_data(y)
         mu, var, logl, info = prob.predict(h)
-        assert info == 0 and np.isfinite(mu).all() and np.isfinite(var).all()
-        res.append((mu, var))
+        assert info == 0 and np.isfinite(mu[:2]).all() and np.isfinite(var[:2]).all()
+        assert np.isnan(mu[2]).all() and np.isnan(var[2]).all()           # no drill rows: the drill property block is not computed (NaN, Q9)
+        res.append((mu[:2], var[:2]))
     scale = max(np.abs(res[0][0]).max(), np.abs(res[1][0]).max())
     assert np.abs(res[2][0] - (2.0 * res[0][0] - 0.5 * res[1][0])).max() < 1e-9 * scale
     assert np.array_equal(res[0][1], res[1][1])                       # variance does not depend on the data

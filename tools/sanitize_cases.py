@@ -78,3 +78,10 @@ if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES) + ["extras"]
     for n in names:
         extras() if n == "extras" else run(n)
+    # give everything back before exit so that memcheck's leak check only reports real leaks (the default context and its buffer
+    # cache otherwise live until the process dies)
+    import gc
+    gc.collect()
+    ctx = _lib.default_context()
+    ctx.release_cache()
+    ctx.close()
