@@ -805,8 +805,14 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             // (transposed digits of all of Pt): the two uses are sequential
             if (p->b8) { gb_dev_free(ctx, p->b8); p->b8 = nullptr; }
             if (p->b_exp) { gb_dev_free(ctx, p->b_exp); p->b_exp = nullptr; }
-            const size_t aka_bytes = 3 * (size_t)ozaki_rows_bytes(Ns, ncp, S, 128);
-            const size_t var_bytes = (size_t)ozaki_cols_bytes(ldp, Mp, S);
+            // (a) row digits of ONE Pt block (M side of an AkA product; the three products run one after the other through it),
+            // (b) transposed digits of a column chunk of Pt (N side of the variance product): the scratch is the larger of (a) and
+            // min(all of Pt, GEOBO_B200_B8_MB, default 12 GB) -- the variance product walks Pt in column chunks of that size
+            const size_t aka_bytes = (size_t)ozaki_rows_bytes(Ns, ncp, S, 128);
+            const size_t var_all = (size_t)ozaki_cols_bytes(ldp, Mp, S);
+            size_t var_budget = (size_t)12288 << 20;
+            if (const char* ev = getenv("GEOBO_B200_B8_MB")) var_budget = (size_t)(atol(ev) > 0 ? atol(ev) : 12288) << 20;
+            const size_t var_bytes = var_all < var_budget ? var_all : var_budget;
             p->b8_bytes = aka_bytes > var_bytes ? aka_bytes : var_bytes;
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->b8, p->b8_bytes));
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->b_exp, (size_t)(ldp > 3 * Ns ? ldp : 3 * Ns) * sizeof(int)));
@@ -838,8 +844,11 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         }
         oa.n[0] = (int)p->n[0]; oa.n[1] = (int)p->n[1]; oa.n[2] = (int)p->n[2];
         // tile-round pacing (default on; GEOBO_B200_TILE_SYNC=0: free-running CTAs)
-        bool pace = true;
-        if (const char* ev = getenv("GEOBO_B200_TILE_SYNC")) pace = atoi(ev) != 0;
+        // GEOBO_B200_TILE_SYNC: 0 = free-running CTAs, 1 = all CTAs start a round together, n > 1 = a CTA may run n - 1 rounds ahead
+        int pace_mode = 1;
+        if (const char* ev = getenv("GEOBO_B200_TILE_SYNC")) pace_mode = atoi(ev);
+        const bool pace = pace_mode > 0;
+        oa.sync_slack = pace_mode > 1 ? pace_mode - 1 : 0;
         oa.sync_ctr = nullptr;
         GB_CUDA(ctx, cudaMemsetAsync(p->sync_ctr, 0, 4 * sizeof(unsigned int), s));
         if (pace) oa.sync_ctr = p->sync_ctr;
@@ -882,8 +891,9 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         const int cc[3][2] = {{0, 0}, {1, 0}, {1, 1}};      // (c', c): block row = Pt rows of c', block column = A_c
         for (int t = 0; t < 3; ++t) {
             const int cp_ = cc[t][0], c = cc[t][1];
-            GB_CUDA(ctx, ozaki_slice_rows(p->Pt + (long)cp_ * Ns * ldp + (long)c * ncp, Ns, ncp, ldp, S, p->b_exp + t * Ns, p->b8 + t * blk, ncp, 128, s));
-            GB_CUDA(ctx, ozaki_gemm_store(p->b8 + t * blk, p->b_exp + t * Ns, ks, 0, p->a8[c], p->a_exp[c], a_ksteps, a_k0, ks, (int)Ns, (int)Ns,
+            (void)blk;           // one block buffer, reused by the three stream-ordered products
+            GB_CUDA(ctx, ozaki_slice_rows(p->Pt + (long)cp_ * Ns * ldp + (long)c * ncp, Ns, ncp, ldp, S, p->b_exp + t * Ns, p->b8, ncp, 128, s));
+            GB_CUDA(ctx, ozaki_gemm_store(p->b8, p->b_exp + t * Ns, ks, 0, p->a8[c], p->a_exp[c], a_ksteps, a_k0, ks, (int)Ns, (int)Ns,
                                           p->Bm + (long)cp_ * Ns * Mp + (long)c * Ns, Mp, c == cp_ ? 1 : 0, S, ctx->sm_count, s));
         }
         p->nlaunch += 9;                  // 3 x (row absmax, row slicing, GEMM)
@@ -1023,8 +1033,19 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         GB_CUDA(ctx, refine_scatter_mu(p->rf_z, ncp, ncol, p->mu, s, nrp));
         if (nref > 0) GB_CUDA(ctx, refine_dot(p->ydev, p->alpha, M, p->scal + 1, s));    // u.u = y^T (AkA)^-1 y with the refined alpha
         GB_CUDA(ctx, ozaki_slice_rows(p->Linv, Mp, Mp, Mp, S, p->l_exp, p->l8, Mp, 128, s));
-        GB_CUDA(ctx, ozaki_slice_cols_mean(p->Pt, Mp, ldp, ldp, S, p->b_exp, p->b8, p->alpha, nullptr, ncp, ncol, s));
-        GB_CUDA(ctx, ozaki_colsumsq_tri(p->l8, p->l_exp, p->b8, p->b_exp, (int)Mp, ldp, S, p->partial, p->vscratch, ctx->sm_count, s));
+        {
+            // column chunks of Pt that fit the digit scratch (multiples of the column-tile width; one chunk for small problems)
+            const long ntc = ozaki_tile_n(S);
+            long qn = (long)(p->b8_bytes / ((size_t)Mp * S)) / ntc * ntc;
+            if (qn < ntc) qn = ntc;
+            for (long q0 = 0; q0 < ldp; q0 += qn) {
+                const long qc = ldp - q0 < qn ? ldp - q0 : qn;
+                GB_CUDA(ctx, ozaki_slice_cols_mean(p->Pt + q0, Mp, qc, ldp, S, p->b_exp + q0, p->b8, p->alpha, nullptr, ncp, ncol, s));
+                GB_CUDA(ctx, ozaki_colsumsq_tri(p->l8, p->l_exp, p->b8, p->b_exp + q0, (int)Mp, qc, S, p->partial + q0, p->vscratch, ctx->sm_count, s, ldp));
+                p->nlaunch += 3;
+            }
+            p->nlaunch -= 3;     // the first chunk is part of the fixed count below
+        }
         GB_CUDA(ctx, cudaEventRecord(p->ev[7], s));
         GB_CUDA(ctx, ozaki_var_finalize(p->partial, (int)(Mp / 128), ldp, ncp, ncol, h->gp_amp, p->var, s, nrp));
         p->nlaunch += 11;                 // u / alpha (2), two dots, mean scatter, 2 x 2 slicing kernels, colsumsq GEMM, variance

@@ -143,6 +143,7 @@ struct OzakiArgs {
     const int* cull;         // [9][2] device: extents (|dy|, |dx|) of the non-zero digits of every table (ozaki_table_extents), or null
     int n[3];                // xN, yN, zN
     unsigned long long* steps_ctr;   // device counter, ZERO at launch: K steps visited (sum over tiles); or null
+    int sync_slack;          // rounds of slack of the pacing (0 = strict)
     unsigned int* sync_ctr;  // device counter, ZERO at launch: tile-round pacing of the copy lanes (keeps the shared K strips in L2); or null
 };
 // cull[2 tb + 0 / 1] = largest |dy| / |dx| lattice offset with a non-zero digit in any plane of table tb (after ozaki_slice_tables)
@@ -169,8 +170,9 @@ long ozaki_cols_bytes(long cols, long kp, int slices);
 cudaError_t ozaki_slice_cols_mean(const double* X, long rows, long cols, long ld, int slices, int* exps, uint8_t* out,
                                   const double* alpha, double* mu, long ncp, long ncol, cudaStream_t s);
 long ozaki_colsumsq_scratch_bytes(int Mp, int slices, int sm_count);
+// ldpart: leading dimension of `partial` ([Mp / 128][ldpart]; 0 = ncols) -- a column chunk of a wider matrix writes into its columns
 cudaError_t ozaki_colsumsq_tri(const uint8_t* a8, const int* a_exp, const uint8_t* b8, const int* b_exp, int Mp, long ncols,
-                               int slices, double* partial, double* scratch, int sm_count, cudaStream_t s);
+                               int slices, double* partial, double* scratch, int sm_count, cudaStream_t s, long ldpart = 0);
 cudaError_t ozaki_gemm_store(const uint8_t* a8, const int* a_exp, int a_ksteps, int a_k0, const uint8_t* b8, const int* b_exp,
                              int b_ksteps, int b_k0, int ksteps, int M, int N, double* C, long ldc, int lower, int slices,
                              int sm_count, cudaStream_t s);

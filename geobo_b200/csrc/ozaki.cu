@@ -150,6 +150,7 @@ struct Params {
     // L2-full of each other.  Left alone they drift apart (measured at 64x64x32: 3.98 TB read from HBM for a 5.4 GB operand), so
     // the copy lanes count arrivals in this device counter and start a round's loads together.  null = no pacing.
     unsigned int* sync_ctr;
+    int sync_slack;                  // rounds a CTA may run ahead of the slowest one (0: all start a round together)
     unsigned long long* steps_ctr;   // += K steps visited (one add per tile), for the roofline accounting; or null
     int n_stile, n_itile;     // sensor-row tiles of NT, voxel-column tiles of 128
 };
@@ -279,10 +280,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
             uint32_t word[2][S];                           // table words of step ks
             int wi[2];
             uint32_t sh[2];
-            auto load_lj = [&](int k, int (&lj)[2]) {          // k: step index t of this tile
-                const int kk = kr.ks((uint32_t)min(k, nt - 1));
+            // K step of tile step t, for the monotone stream t = ks, ks + PROD_SLOTS, ks + 2 PROD_SLOTS, ... of this warp: running
+            // (row, step inside the row window) instead of a division per step (this warp sits on the done -> st -> full chain)
+            int lj_row = 0, lj_q = 0, lj_t = 0;
+            const int lj_last = nt > 0 ? kr.ks((uint32_t)(nt - 1)) : 0;
+            auto load_lj = [&](int (&lj)[2]) {
+                const int kk = lj_t < nt ? (kr.jya + lj_row) * kr.rowsteps + kr.koff + lj_q : lj_last;
                 lj[0] = P.L[kk * 32];
                 lj[1] = P.L[kk * 32 + 16];
+                lj_t += PROD_SLOTS;
+                lj_q += PROD_SLOTS;
+                while (lj_q >= kr.w) { lj_q -= kr.w; ++lj_row; }
             };
             auto load_words = [&](const int (&lj)[2]) {
 #pragma unroll
@@ -297,9 +305,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
                 }
             };
             {
+                lj_t = ks;
+                lj_row = ks / kr.w;                 // one division per tile
+                lj_q = ks - lj_row * kr.w;
                 int lj0[2];
-                load_lj(ks, lj0);
-                load_lj(ks + PROD_SLOTS, lj_nn);
+                load_lj(lj0);                       // step ks
+                load_lj(lj_nn);                     // step ks + PROD_SLOTS
                 load_words(lj0);
             }
             for (; ks < nt; ks += PROD_SLOTS) {                // ks: step index t of this tile (kr.ks(t) = K step)
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
                 // ---- prefetch: table words of the next own step, lattice ids of the one after
                 {
                     int ljn[2] = {lj_nn[0], lj_nn[1]};
-                    load_lj(ks + 2 * PROD_SLOTS, lj_nn);
+                    load_lj(lj_nn);                 // step ks + 2 PROD_SLOTS
                     load_words(ljn);
                 }
                 // ---- the TMEM buffer (it % NABUF) is free once the MMAs of step it - NABUF have completed
@@ -345,14 +356,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
         // =============================================================== sensitivity-digit copies (one elected lane)
         if (lane == 0) {
             uint32_t it = 0;
-            unsigned int target = 0;
             for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 if (P.sync_ctr) {
-                    // all CTAs are co-resident (grid <= SM count, one CTA per SM), so waiting on the others cannot deadlock
-                    const long first = tile - blockIdx.x;                                   // first tile of this round
-                    target += (unsigned int)min((long)gridDim.x, ntiles - first);           // arrivals up to and including this round
+                    // all CTAs are co-resident (grid <= SM count, one CTA per SM), so waiting on the others cannot deadlock.
+                    // Arrivals up to and including round k: min(ntiles, (k + 1) gridDim.x).  A CTA entering round k waits until
+                    // every CTA has entered round k - slack.
+                    const long k = (tile - blockIdx.x) / gridDim.x - P.sync_slack;
                     atomicAdd(P.sync_ctr, 1u);
-                    while (*(volatile unsigned int*)P.sync_ctr < target) __nanosleep(256);
+                    if (k >= 0) {
+                        const unsigned int target = (unsigned int)min(ntiles, (k + 1) * (long)gridDim.x);
+                        while (*(volatile unsigned int*)P.sync_ctr < target) __nanosleep(256);
+                    }
                 }
                 const int tq = (int)(tile / tiles_per_task);
                 const int stile = (int)((tile % tiles_per_task) / P.n_itile);
@@ -586,6 +600,7 @@ cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStre
     P.nr = a.nr == 2 ? 2 : 3;
     P.cull = a.cull;
     P.sync_ctr = a.sync_ctr;
+    P.sync_slack = a.sync_slack;
     P.steps_ctr = a.steps_ctr;
     P.xN = a.n[0]; P.yN = a.n[1]; P.zN = a.n[2];
     P.chunk = ozaki_chunk();

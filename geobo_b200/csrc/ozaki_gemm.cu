@@ -356,10 +356,10 @@ long ozaki_colsumsq_scratch_bytes(int Mp, int slices, int sm_count) {
 }
 
 cudaError_t ozaki_colsumsq_tri(const uint8_t* a8, const int* a_exp, const uint8_t* b8, const int* b_exp, int Mp, long ncols, int slices,
-                               double* partial, double* scratch, int sm_count, cudaStream_t s) {
+                               double* partial, double* scratch, int sm_count, cudaStream_t s, long ldpart) {
     ozaki::GemmParams P;
     memset(&P, 0, sizeof P);
-    P.a8 = a8; P.a_exp = a_exp; P.b8 = b8; P.b_exp = b_exp; P.partial = partial; P.ldc = ncols;
+    P.a8 = a8; P.a_exp = a_exp; P.b8 = b8; P.b_exp = b_exp; P.partial = partial; P.ldc = ldpart > 0 ? ldpart : ncols;
     P.M = Mp; P.N = (int)ncols;
     P.a_ksteps = P.b_ksteps = P.ksteps = Mp / 32;
     P.chunk_steps = ozaki_chunk() / 32;

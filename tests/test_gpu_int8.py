@@ -142,6 +142,21 @@ def test_zero_digit_culling_and_tile_pacing_are_bitwise_neutral(ctx, monkeypatch
     print("projection ms: every K step %.3f, culled %.3f" % (t0, inv1.timings["project"]))
 
 
+def test_variance_product_in_column_chunks_is_bitwise_neutral(ctx, monkeypatch):
+    """GEOBO_B200_B8_MB=1: the transposed digit blocks of Pt (N side of colsumsq(Linv . Pt)) are built and multiplied in column
+    chunks through a small scratch (at 128x128x64 all of them would take 65 GB per GPU); per column nothing changes."""
+    c = configure(base_cfg(), xNcube=12, yNcube=11, zNcube=32, kernelfunc="matern32", precision="int8x5")
+    f = synthetic_inputs(c, 6)
+    gl = c.gp_lengthscale * c.xvoxsize * np.array([1.0, 1.01, 1.02])
+    inv0, out0 = run_cubing(f, gl=gl.copy())
+    launches0 = inv0.timings["launches"]
+    monkeypatch.setenv("GEOBO_B200_B8_MB", "1")
+    inv1, out1 = run_cubing(f, gl=gl.copy())
+    assert inv1.timings["launches"] > launches0                       # several chunks ran
+    for n, a, b in zip(CUBES, out0, out1):
+        assert np.array_equal(a, b), n
+
+
 def test_int8_full_size_32cube_vs_fp64_path(ctx):
     """BASELINE config 2 size (N = 32768, M = 2048, exp kernel, cond ~ 1e6): slice path against the fp64 DMMA path
     on the same device problem, plus linearity of the mean in the data."""
