@@ -349,6 +349,7 @@ struct gb_problem {
     int* t_exp = nullptr;
     unsigned int* sync_ctr = nullptr;    // [4] words: [0] arrival counter of the projection kernel's tile rounds, [2..3] K steps visited (u64)
     double ksteps_total = 0.0;           // K steps of the last projection launch without culling (tiles x steps)
+    int* tile_perm = nullptr;            // [2][6][ceil(ncol / 128)] sorted tile order of the projection kernel + its keys
     int* cull_ext = nullptr;             // [9][2] extents of the non-zero table digits (zero-digit culling of the projection's K steps)
     int a8_slices = 0;
     // int8 variance path: explicit Linv, its digit blocks, transposed digit blocks of Pt, per-row-tile column sums of squares
@@ -405,7 +406,7 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
-                    p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp, p->cull_ext, p->sync_ctr,
+                    p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp, p->cull_ext, p->sync_ctr, p->tile_perm,
                     p->Linv, p->tmpL, p->alpha, p->l8, p->l_exp, p->b8, p->b_exp, p->partial,
                     p->edges_dev, p->loc_dev, p->Achunk[0], p->Achunk[1], p->a_amax,
                     p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch, p->chol_stage, p->chol_pan, p->chol_paninfo, p->kron_f, p->kron_T, p->fft_W, p->fft_tw, p->fft_scratch,
@@ -801,6 +802,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             if (!p->t_exp) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->t_exp, 16 * sizeof(int)));
             if (!p->cull_ext) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->cull_ext, 18 * sizeof(int)));
             if (!p->sync_ctr) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->sync_ctr, 4 * sizeof(unsigned int)));
+            if (!p->tile_perm) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->tile_perm, (size_t)2 * 6 * ((ncol + 127) / 128) * sizeof(int)));
             // digit scratch shared by the AkA products (row digits of three Pt blocks) and the variance product
             // (transposed digits of all of Pt): the two uses are sequential
             if (p->b8) { gb_dev_free(ctx, p->b8); p->b8 = nullptr; }
@@ -849,6 +851,11 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         if (const char* ev = getenv("GEOBO_B200_TILE_SYNC")) pace_mode = atoi(ev);
         const bool pace = pace_mode > 0;
         oa.sync_slack = pace_mode > 1 ? pace_mode - 1 : 0;
+        // GEOBO_B200_TILE_SORT=0: natural tile order (default: tiles of a round sorted to equal K-step counts)
+        bool tsort = true;
+        if (const char* ev = getenv("GEOBO_B200_TILE_SORT")) tsort = atoi(ev) != 0;
+        oa.perm_scratch = tsort ? p->tile_perm : nullptr;
+        if (tsort && cull) p->nlaunch += 2;
         oa.sync_ctr = nullptr;
         GB_CUDA(ctx, cudaMemsetAsync(p->sync_ctr, 0, 4 * sizeof(unsigned int), s));
         if (pace) oa.sync_ctr = p->sync_ctr;

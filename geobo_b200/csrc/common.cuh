@@ -144,6 +144,7 @@ struct OzakiArgs {
     int n[3];                // xN, yN, zN
     unsigned long long* steps_ctr;   // device counter, ZERO at launch: K steps visited (sum over tiles); or null
     int sync_slack;          // rounds of slack of the pacing (0 = strict)
+    int* perm_scratch;       // [2][6][ceil(ncol / 128)] ints (tile order sorted by K-step count + keys), or null = natural tile order
     unsigned int* sync_ctr;  // device counter, ZERO at launch: tile-round pacing of the copy lanes (keeps the shared K strips in L2); or null
 };
 // cull[2 tb + 0 / 1] = largest |dy| / |dx| lattice offset with a non-zero digit in any plane of table tb (after ozaki_slice_tables)

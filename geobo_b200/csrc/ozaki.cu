@@ -151,6 +151,10 @@ struct Params {
     // the copy lanes count arrivals in this device counter and start a round's loads together.  null = no pacing.
     unsigned int* sync_ctr;
     int sync_slack;                  // rounds a CTA may run ahead of the slowest one (0: all start a round together)
+    // tile order: with culling the tiles of one round have different numbers of K steps (cube edges), and paced CTAs would wait
+    // for the longest one.  perm[tq * n_itile + pos] = voxel-column tile handled at position pos of task tq, sorted by decreasing
+    // step count, so that the (up to) gridDim.x tiles of a round cost the same.  null = natural order.
+    const int* perm;
     unsigned long long* steps_ctr;   // += K steps visited (one add per tile), for the roofline accounting; or null
     int n_stile, n_itile;     // sensor-row tiles of NT, voxel-column tiles of 128
 };
@@ -207,6 +211,29 @@ __global__ void table_extent_kernel(const uint8_t* __restrict__ t8, long ext, in
     const int dx = (int)(t % EX) - (xN - 1), dy = (int)(t / EX) - (yN - 1);
     atomicMax(out + 2 * tb, abs(dy));
     atomicMax(out + 2 * tb + 1, abs(dx));
+}
+
+// voxel-column tile at position `pos` of task tq
+__device__ __forceinline__ int tile_at(const Params& P, int tq, int pos) { return P.perm ? P.perm[(long)tq * P.n_itile + pos] : pos; }
+
+// keys[tq][i] = K steps of voxel-column tile i in task tq
+__global__ void tile_steps_kernel(const Params P, int ksteps, int* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, tq = blockIdx.y;
+    if (i < P.n_itile) keys[(long)tq * P.n_itile + i] = (int)tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, i, ksteps).nt;
+}
+
+// perm[tq][rank of i] = i, rank by decreasing key (ties: increasing i) -- n_itile is a few thousand: a rank by counting is enough
+__global__ void tile_rank_kernel(const int* __restrict__ keys, int n, int* __restrict__ perm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, tq = blockIdx.y;
+    if (i >= n) return;
+    const int* k = keys + (long)tq * n;
+    const int ki = k[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+        const int kj = k[j];
+        rank += (kj > ki) || (kj == ki && j < i);
+    }
+    perm[(long)tq * n + rank] = i;
 }
 
 constexpr int PROD_SLOTS = 3;                          // producer warps per TMEM lane quarter
@@ -266,7 +293,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int tq = (int)(tile / tiles_per_task);
             const int task = (tq / P.nr) * 3 + tq % P.nr;             // c * 3 + r
-            const int itile = (int)((tile % tiles_per_task) % P.n_itile);
+            const int itile = tile_at(P, tq, (int)((tile % tiles_per_task) % P.n_itile));
             const KRange kr = tile_krange(P, task, itile, ksteps);
             const int nt = (int)kr.nt;
             const int i0 = itile * 128 + 32 * q4 + (lane & 16);       // first voxel column of this half-warp's segment
@@ -371,7 +398,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
                 const int tq = (int)(tile / tiles_per_task);
                 const int stile = (int)((tile % tiles_per_task) / P.n_itile);
                 const uint8_t* src = P.a8[tq / P.nr] + (size_t)stile * ksteps * B_BYTES;
-                const KRange kr = tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, (int)((tile % tiles_per_task) % P.n_itile), ksteps);
+                const KRange kr = tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, tile_at(P, tq, (int)((tile % tiles_per_task) % P.n_itile)), ksteps);
                 if (P.steps_ctr) atomicAdd(P.steps_ctr, (unsigned long long)kr.nt);
                 for (int jj = 0; jj < kr.nrows; ++jj) {
                     const uint8_t* rowsrc = src + (size_t)((kr.jya + jj) * kr.rowsteps + kr.koff) * B_BYTES;
@@ -400,7 +427,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
             uint64_t* db = done_bar;
             for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int tq = (int)(tile / tiles_per_task);
-                const int nt = (int)tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, (int)((tile % tiles_per_task) % P.n_itile), ksteps).nt;
+                const int nt = (int)tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, tile_at(P, tq, (int)((tile % tiles_per_task) % P.n_itile)), ksteps).nt;
                 for (int k0 = 0; k0 < nt; k0 += chunk_steps, ++chunk_id) {
                     const int k1 = min(nt, k0 + chunk_steps);
                     mbar_wait(&tempty_bar, (chunk_id & 1) ^ 1);     // epilogue has drained the accumulators
@@ -438,7 +465,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int tq = (int)(tile / tiles_per_task);
             const long rem = tile % tiles_per_task;
-            const int stile = (int)(rem / P.n_itile), itile = (int)(rem % P.n_itile);
+            const int stile = (int)(rem / P.n_itile), itile = tile_at(P, tq, (int)(rem % P.n_itile));
             const int c = tq / P.nr, r = tq % P.nr, task = c * 3 + r;
             const int s0 = stile * NT, i = itile * 128 + m;
             const bool col_ok = i < P.ncol;
@@ -481,7 +508,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
 }
 
 template <int S>
-static cudaError_t launch_one(const Params& P, int sm_count, cudaStream_t s) {
+static cudaError_t launch_one(const Params& P, int sm_count, cudaStream_t s, int* perm_scratch) {
     constexpr int NT = Cfg<S>::NTP;
     constexpr int smem = ring_stages<S>() * S * NT * 32;
     cudaError_t e = cudaFuncSetAttribute(ozaki_project_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -491,6 +518,16 @@ static cudaError_t launch_one(const Params& P, int sm_count, cudaStream_t s) {
     q.n_itile = (P.ncol + 127) / 128;
     const long ntiles = 2L * q.nr * q.n_stile * q.n_itile;
     const int grid = (int)(ntiles < (long)sm_count ? ntiles : (long)sm_count);
+    if (q.cull && perm_scratch) {
+        // sorted tile order (only matters when tiles differ, i.e. with culling): keys in the second half of the scratch
+        int* keys = perm_scratch + (long)2 * q.nr * q.n_itile;
+        dim3 g((unsigned)((q.n_itile + 127) / 128), (unsigned)(2 * q.nr));
+        tile_steps_kernel<<<g, 128, 0, s>>>(q, (int)(q.kp / 32), keys);
+        tile_rank_kernel<<<g, 128, 0, s>>>(keys, q.n_itile, perm_scratch);
+        q.perm = perm_scratch;
+    } else {
+        q.perm = nullptr;
+    }
     ozaki_project_kernel<S><<<grid, TS_THREADS, smem, s>>>(q);
     return cudaGetLastError();
 }
@@ -601,15 +638,16 @@ cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStre
     P.cull = a.cull;
     P.sync_ctr = a.sync_ctr;
     P.sync_slack = a.sync_slack;
+    P.perm = nullptr;
     P.steps_ctr = a.steps_ctr;
     P.xN = a.n[0]; P.yN = a.n[1]; P.zN = a.n[2];
     P.chunk = ozaki_chunk();
     P.n_stile = 0;
     P.n_itile = 0;
     switch (slices) {
-        case 4: return ozaki::launch_one<4>(P, sm_count, s);
-        case 5: return ozaki::launch_one<5>(P, sm_count, s);
-        case 6: return ozaki::launch_one<6>(P, sm_count, s);
+        case 4: return ozaki::launch_one<4>(P, sm_count, s, a.perm_scratch);
+        case 5: return ozaki::launch_one<5>(P, sm_count, s, a.perm_scratch);
+        case 6: return ozaki::launch_one<6>(P, sm_count, s, a.perm_scratch);
     }
     return cudaErrorInvalidValue;
 }

@@ -131,10 +131,14 @@ def test_zero_digit_culling_and_tile_pacing_are_bitwise_neutral(ctx, monkeypatch
     inv1, out1 = run_cubing(f, gl=gl.copy())
     monkeypatch.setenv("GEOBO_B200_TILE_SYNC", "1")
     inv2, out2 = run_cubing(f, gl=gl.copy())
-    for n, a, b, d in zip(CUBES, out0, out1, out2):
+    monkeypatch.setenv("GEOBO_B200_TILE_SYNC", "2")          # one round of slack
+    monkeypatch.setenv("GEOBO_B200_TILE_SORT", "0")          # natural tile order instead of the order sorted by K-step count
+    inv3, out3 = run_cubing(f, gl=gl.copy())
+    for n, a, b, d, e in zip(CUBES, out0, out1, out2, out3):
         assert np.array_equal(a, b, equal_nan=True), n
         assert np.array_equal(a, d, equal_nan=True), n
-    assert inv0.logl == inv1.logl == inv2.logl
+        assert np.array_equal(a, e, equal_nan=True), n
+    assert inv0.logl == inv1.logl == inv2.logl == inv3.logl
     with np.errstate(all="ignore"):
         ref, ex = o.cubing_lean(c, f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"], gp_length=gl.copy())
     for n, a, r in zip(CUBES, out2, ref):
