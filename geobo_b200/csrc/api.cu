@@ -352,6 +352,8 @@ struct gb_problem {
     int* tile_perm = nullptr;            // [2][6][ceil(ncol / 128)] sorted tile order of the projection kernel + its keys
     int* cull_ext = nullptr;             // [9][2] extents of the non-zero table digits (zero-digit culling of the projection's K steps)
     int a8_slices = 0;
+    int a8_scope = 0;                    // 0: not built; 1: all N contraction columns (dense projection + AkA); 2: only this rank's voxel
+                                         // columns (lean + structured projection: the digits are then only the N side of the AkA products)
     // int8 variance path: explicit Linv, its digit blocks, transposed digit blocks of Pt, per-row-tile column sums of squares
     double* Linv = nullptr;              // [Mp][Mp]
     double* tmpL = nullptr;              // [128][Mp]
@@ -718,9 +720,9 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
     const FftGeom fg = fft_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1);
     const KronGeom kg = kron_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1);
     const StencilGeom sg = stencil_geom(p->n[0], p->n[1], p->n[2], p->c0, p->c1, p->vox, h->gp_length);
-    if (p->lean && (h->slices == 0 || structured))
-        return gb_fail(ctx, GB_ERR_UNSUPPORTED, "this problem keeps no resident fp64 sensitivities (lean mode, %lld x %lld): only the dense int8 "
-                       "tensor-core path (slices = 4, 5, 6; structure = dense) runs on it; set GEOBO_B200_LEAN_A=0 if the matrices fit",
+    if (p->lean && h->slices == 0)
+        return gb_fail(ctx, GB_ERR_UNSUPPORTED, "this problem keeps no resident fp64 sensitivities (lean mode, %lld x %lld): only the int8 "
+                       "tensor-core paths (slices = 4, 5, 6) run on it; set GEOBO_B200_LEAN_A=0 if the matrices fit",
                        (long long)p->Ns, (long long)p->N);
     if (compact && h->kernel_id != GB_KERNEL_SPARSE)
         return gb_fail(ctx, GB_ERR_UNSUPPORTED, "structure = compact needs kernelfunc 'sparse': only the compact-support kernels (kernels.py:101-138) "
@@ -768,10 +770,15 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         if (p->n[2] % 16 != 0 || ncol % 16 != 0)
             return gb_fail(ctx, GB_ERR_UNSUPPORTED, "the int8 tensor-core path needs zNcube %% 16 == 0 and a voxel-column shard that is a multiple of 16 "
                            "(got zNcube=%lld, columns=%ld); use slices = 0", (long long)p->n[2], ncol);
-        if (p->a8_slices != S) {   // digit planes of the sensitivities: built once per problem and slice count
+        // scope of the digit blocks: the dense projection contracts over all N columns; with a structured projection on a lean
+        // problem they are only the N side of the AkA products, i.e. this rank's voxel columns (128x128x64: 21 GB instead of 172)
+        const int want_scope = (p->lean && structured) ? 2 : 1;
+        if (p->a8_slices != S || (p->a8_scope != want_scope && !(p->a8_scope == 1 && want_scope == 2))) {
+            // digit planes of the sensitivities: built once per problem, slice count and scope
+            const long a8_kp = want_scope == 2 ? ncp : p->Kp;
             for (int c = 0; c < 2; ++c) {
                 if (p->a8[c]) { gb_dev_free(ctx, p->a8[c]); p->a8[c] = nullptr; }
-                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a8[c], (size_t)ozaki_rows_bytes(Ns, p->Kp, S, ozaki_tile_np(S))));
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a8[c], (size_t)ozaki_rows_bytes(Ns, a8_kp, S, ozaki_tile_np(S))));
                 if (!p->a_exp[c]) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a_exp[c], (size_t)Ns * sizeof(int)));
                 if (!p->lean) GB_CUDA(ctx, ozaki_slice_sens(p->A[c], Ns, p->N, p->lda, S, p->a_exp[c], p->a8[c], p->Kp, s));
             }
@@ -787,16 +794,23 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
                 }));
                 for (int c = 0; c < 2; ++c) {
                     GB_CUDA(ctx, ozaki_exps_from_absmax(p->a_amax + c * Ns, Ns, p->a_exp[c], s));
-                    GB_CUDA(ctx, cudaMemsetAsync(p->a8[c], 0, (size_t)ozaki_rows_bytes(Ns, p->Kp, S, ozaki_tile_np(S)), s));
+                    GB_CUDA(ctx, cudaMemsetAsync(p->a8[c], 0, (size_t)ozaki_rows_bytes(Ns, a8_kp, S, ozaki_tile_np(S)), s));
                 }
                 GB_TRY(lean_for_each_chunk(p, [&](int64_t j0, int64_t ncols) -> cudaError_t {
+                    // columns [ja, jb) of this chunk go into the digit blocks: all of them, or the part inside this rank's shard
+                    const int64_t ja = want_scope == 2 ? std::max<int64_t>(j0, p->c0) : j0;
+                    const int64_t jb = want_scope == 2 ? std::min<int64_t>(j0 + ncols, p->c1) : j0 + ncols;
+                    if (jb <= ja) return cudaSuccess;
+                    const int64_t kbase = want_scope == 2 ? p->c0 : 0;
                     for (int c = 0; c < 2; ++c) {
-                        cudaError_t e = ozaki_slice_rows_range(p->Achunk[c], Ns, ncols, p->chunk_ld, S, p->a_exp[c], p->a8[c], p->Kp, ozaki_tile_np(S), j0 / 32, s);
+                        cudaError_t e = ozaki_slice_rows_range(p->Achunk[c] + (ja - j0), Ns, jb - ja, p->chunk_ld, S, p->a_exp[c], p->a8[c], a8_kp,
+                                                               ozaki_tile_np(S), (ja - kbase) / 32, s);
                         if (e != cudaSuccess) return e;
                     }
                     return cudaSuccess;
                 }));
             }
+            p->a8_scope = want_scope;
             if (p->t8) { gb_dev_free(ctx, p->t8); p->t8 = nullptr; }
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->t8, (size_t)ozaki_table_bytes(p->ext, S)));
             if (!p->t_exp) GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->t_exp, 16 * sizeof(int)));
@@ -818,7 +832,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             p->b8_bytes = aka_bytes > var_bytes ? aka_bytes : var_bytes;
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->b8, p->b8_bytes));
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->b_exp, (size_t)(ldp > 3 * Ns ? ldp : 3 * Ns) * sizeof(int)));
-            p->bytes += 2 * (size_t)ozaki_rows_bytes(Ns, p->Kp, S, ozaki_tile_np(S)) + p->b8_bytes;
+            p->bytes += 2 * (size_t)ozaki_rows_bytes(Ns, a8_kp, S, ozaki_tile_np(S)) + p->b8_bytes;
             p->a8_slices = S;
         }
     }
@@ -826,7 +840,25 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         // fft: zero-padded 3-D FFT convolutions with the stationary tables (any kernel)
         // kron: three Toeplitz mode products per block (rows of A_c -> y mode into the L2-resident scratch -> z and x modes -> rows of Pt)
         // compact: tap sum over the support window of the compact kernels
-        for (int c = 0; c < 2; ++c) GB_CUDA(ctx, apply_structured(c * 3, p->A[c], p->lda, Ns, p->Pt + (long)c * Ns * ldp, ldp, 0));
+        if (!p->lean) {
+            for (int c = 0; c < 2; ++c) GB_CUDA(ctx, apply_structured(c * 3, p->A[c], p->lda, Ns, p->Pt + (long)c * Ns * ldp, ldp, 0));
+        } else {
+            // lean problem: the rows of A_c are regenerated in sensor-row chunks (full width) through the chunk buffer
+            const double zeroB[3] = {0.0, 0.0, 0.0};
+            long rows_chunk = (long)((p->Ns * p->chunk_ld) / p->lda);
+            if (rows_chunk < 1) return gb_fail(ctx, GB_ERR_UNSUPPORTED, "lean chunk buffer smaller than one sensitivity row; raise GEOBO_B200_LEAN_CHUNK_MB");
+            if (const char* ev = getenv("GEOBO_B200_LEAN_ROW_CHUNK")) { const long v = atol(ev); if (v >= 1 && v < rows_chunk) rows_chunk = v; }
+            for (int c = 0; c < 2; ++c)
+                for (long s0 = 0; s0 < Ns; s0 += rows_chunk) {
+                    const long nrow = Ns - s0 < rows_chunk ? Ns - s0 : rows_chunk;
+                    GB_CUDA(ctx, cudaMemsetAsync(p->Achunk[0], 0, (size_t)nrow * p->lda * sizeof(double), s));      // pad columns of the rows
+                    GB_CUDA(ctx, launch_a_sens_range(c == 0 ? GB_SENS_GRAV : GB_SENS_MAGN, c == 0 ? zeroB : p->Bfield, p->loc_dev + 3 * s0, nrow, p->edges_dev,
+                                                     p->n, c == 0 ? p->grav_mul : p->magn_mul, c == 0 ? p->grav_div : p->magn_div, p->Achunk[0], p->lda, 0,
+                                                     (int)p->n[1], ctx->sm_count, s));
+                    GB_CUDA(ctx, apply_structured(c * 3, p->Achunk[0], p->lda, nrow, p->Pt + ((long)c * Ns + s0) * ldp, ldp, 0));
+                    p->nlaunch += 1;
+                }
+        }
     } else if (h->slices != 0) {
         const int S = h->slices;
         GB_CUDA(ctx, ozaki_slice_tables(p->tables, p->ext, S, p->t_exp, p->t8, s));
@@ -846,8 +878,10 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         }
         oa.n[0] = (int)p->n[0]; oa.n[1] = (int)p->n[1]; oa.n[2] = (int)p->n[2];
         // tile-round pacing (default on; GEOBO_B200_TILE_SYNC=0: free-running CTAs)
-        // GEOBO_B200_TILE_SYNC: 0 = free-running CTAs, 1 = all CTAs start a round together, n > 1 = a CTA may run n - 1 rounds ahead
-        int pace_mode = 1;
+        // GEOBO_B200_TILE_SYNC: 0 = free-running CTAs, 1 = all CTAs start a round together, n > 1 = a CTA may run n - 1 rounds ahead.
+        // Default 2 (measured on the 64x64x32 and 32^3 cubes, profiles/r2_bench_f_*.json: one round of slack absorbs what the sorted
+        // tile order leaves of the edge-tile imbalance and keeps the HBM traffic of the launch near the strict setting's)
+        int pace_mode = 2;
         if (const char* ev = getenv("GEOBO_B200_TILE_SYNC")) pace_mode = atoi(ev);
         const bool pace = pace_mode > 0;
         oa.sync_slack = pace_mode > 1 ? pace_mode - 1 : 0;
@@ -894,7 +928,8 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         // reused (K steps c0/32 ..).  Lower triangle: blocks (0,0) and (1,1) lower, (1,0) full.
         const int S = h->slices;
         const size_t blk = (size_t)ozaki_rows_bytes(Ns, ncp, S, 128);
-        const int a_ksteps = (int)(p->Kp / 32), a_k0 = (int)(p->c0 / 32), ks = (int)(ncp / 32);
+        // N side = the sensitivities' digit blocks: K steps c0 / 32 .. of the full-width blocks, or the shard-only blocks from step 0
+        const int a_ksteps = p->a8_scope == 2 ? (int)(ncp / 32) : (int)(p->Kp / 32), a_k0 = p->a8_scope == 2 ? 0 : (int)(p->c0 / 32), ks = (int)(ncp / 32);
         const int cc[3][2] = {{0, 0}, {1, 0}, {1, 1}};      // (c', c): block row = Pt rows of c', block column = A_c
         for (int t = 0; t < 3; ++t) {
             const int cp_ = cc[t][0], c = cc[t][1];
@@ -963,10 +998,8 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         //   reduction in the epilogue (:117, diag only).
         const int S = h->slices;
         if (p->var_slices != S) {
-            if (p->l8) { gb_dev_free(ctx, p->l8); p->l8 = nullptr; }
             if (!p->Linv) {
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->Linv, (size_t)Mp * Mp * sizeof(double)));
-                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->tmpL, (size_t)Mp * Mp * sizeof(double)));
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->alpha, (size_t)Mp * sizeof(double)));
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->l_exp, (size_t)Mp * sizeof(int)));
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->partial, (size_t)(Mp / 128) * ldp * sizeof(double)));
@@ -975,16 +1008,27 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_part, (size_t)16 * p->Kp * sizeof(double)));
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->rf_t, (size_t)3 * Mp * sizeof(double)));
                 GB_CUDA(ctx, cudaMemsetAsync(p->rf_t, 0, (size_t)3 * Mp * sizeof(double), s));
-                p->bytes += 2 * (size_t)Mp * Mp * 8 + (size_t)(Mp / 128) * ldp * 8;
+                p->bytes += (size_t)Mp * Mp * 8 + (size_t)(Mp / 128) * ldp * 8;
             }
-            GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->l8, (size_t)ozaki_rows_bytes(Mp, Mp, S)));
             if (p->vscratch) { gb_dev_free(ctx, p->vscratch); p->vscratch = nullptr; }
             if (ozaki_colsumsq_scratch_bytes((int)Mp, S, ctx->sm_count))
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->vscratch, (size_t)ozaki_colsumsq_scratch_bytes((int)Mp, S, ctx->sm_count)));
-            p->bytes += (size_t)ozaki_rows_bytes(Mp, Mp, S);
             p->var_slices = S;
         }
-        GB_CUDA(ctx, chol_inverse(p->Bm, Mp, (int)Mp, w, p->Linv, p->tmpL, s, &p->nlaunch));
+        // Two buffers of this stage live inside others whose contents are dead by then (at 128x128x64 they would be 8.7 + 5.4 GB):
+        //  * the Mp x Mp scratch of the triangular inverse sits in the digit scratch b8 (idle between the AkA products and the
+        //    variance product) when that is large enough, else in its own allocation;
+        //  * the digit blocks of Linv (Mp^2 S bytes) sit in Bm: the factor L is not read again once Linv exists.
+        double* tmpL = reinterpret_cast<double*>(p->b8);
+        if (p->b8_bytes < (size_t)Mp * Mp * sizeof(double)) {
+            if (!p->tmpL) {
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->tmpL, (size_t)Mp * Mp * sizeof(double)));
+                p->bytes += (size_t)Mp * Mp * 8;
+            }
+            tmpL = p->tmpL;
+        }
+        uint8_t* l8 = reinterpret_cast<uint8_t*>(p->Bm);
+        GB_CUDA(ctx, chol_inverse(p->Bm, Mp, (int)Mp, w, p->Linv, tmpL, s, &p->nlaunch));
         // u = Linv y (:105), u.u for logl, alpha = L^-T u -- then refined against the fp64 matrix-free operator
         // (the factor came from digit-rounded operands)
         double* rt0 = p->rf_t + 2 * Mp;
@@ -1039,7 +1083,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         }
         GB_CUDA(ctx, refine_scatter_mu(p->rf_z, ncp, ncol, p->mu, s, nrp));
         if (nref > 0) GB_CUDA(ctx, refine_dot(p->ydev, p->alpha, M, p->scal + 1, s));    // u.u = y^T (AkA)^-1 y with the refined alpha
-        GB_CUDA(ctx, ozaki_slice_rows(p->Linv, Mp, Mp, Mp, S, p->l_exp, p->l8, Mp, 128, s));
+        GB_CUDA(ctx, ozaki_slice_rows(p->Linv, Mp, Mp, Mp, S, p->l_exp, l8, Mp, 128, s));
         {
             // column chunks of Pt that fit the digit scratch (multiples of the column-tile width; one chunk for small problems)
             const long ntc = ozaki_tile_n(S);
@@ -1048,7 +1092,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             for (long q0 = 0; q0 < ldp; q0 += qn) {
                 const long qc = ldp - q0 < qn ? ldp - q0 : qn;
                 GB_CUDA(ctx, ozaki_slice_cols_mean(p->Pt + q0, Mp, qc, ldp, S, p->b_exp + q0, p->b8, p->alpha, nullptr, ncp, ncol, s));
-                GB_CUDA(ctx, ozaki_colsumsq_tri(p->l8, p->l_exp, p->b8, p->b_exp + q0, (int)Mp, qc, S, p->partial + q0, p->vscratch, ctx->sm_count, s, ldp));
+                GB_CUDA(ctx, ozaki_colsumsq_tri(l8, p->l_exp, p->b8, p->b_exp + q0, (int)Mp, qc, S, p->partial + q0, p->vscratch, ctx->sm_count, s, ldp));
                 p->nlaunch += 3;
             }
             p->nlaunch -= 3;     // the first chunk is part of the fixed count below

@@ -108,7 +108,20 @@ def test_lean_mode_regenerated_sensitivities_match_resident_ones(ctx, monkeypatc
         ref, ex = o.cubing_lean(c, f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"], gp_length=gl.copy())
     for n, a, r in zip(CUBES, out1, ref):
         assert normwise_err(a, r) < 1e-6, n
-    # the fp64 path and the structured projections need resident rows: refused loudly on a lean problem
+    # structured projections on a lean problem: the rows are regenerated in sensor-row chunks (7 rows here: ragged), and only the
+    # digits of this rank's voxel columns are kept (N side of the AkA products)
+    structure = {"exp": "kron", "sparse": "compact", "matern32": "fft"}[kf]
+    monkeypatch.setenv("GEOBO_B200_LEAN_ROW_CHUNK", "7")
+    configure(base_cfg(), xNcube=shape[0], yNcube=shape[1], zNcube=shape[2], kernelfunc=kf, precision="int8x5", structure=structure)
+    inv2, out2 = run_cubing(f, gl=gl.copy())
+    for n, a, r in zip(CUBES, out2, ref):
+        assert normwise_err(a, r) < 1e-6, n
+    monkeypatch.setenv("GEOBO_B200_LEAN_A", "0")
+    inv3, out3 = run_cubing(f, gl=gl.copy())
+    for n, a, b in zip(CUBES, out2, out3):
+        assert normwise_err(a, b) < 1e-11, n
+    monkeypatch.setenv("GEOBO_B200_LEAN_A", "1")
+    # the fp64 path needs resident rows: refused loudly on a lean problem
     configure(base_cfg(), xNcube=shape[0], yNcube=shape[1], zNcube=shape[2], kernelfunc=kf, precision="fp64")
     with pytest.raises(_lib.GeoboB200Error) as e:
         run_cubing(f, gl=gl.copy())
