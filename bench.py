@@ -370,6 +370,32 @@ def run_ours(args):
            "includes": "device problem build (A_sens x2 on GPU), H2D of data/geometry, predict3 stage, D2H of 6 cubes"}
     finite = bool(all(np.isfinite(cb).all() for cb in cubes[:2]))
     parity = parity_vs_fixture(fixture, cubes, inv2.logl, N) if fixture is not None else None
+    # size-independent checks on the full cubes (every workload, also where no CPU fixture of that size exists): the posterior
+    # variance lies in [0, prior variance] voxel by voxel (prior = gp_amp x data std^2), the cubes are finite (NaN drill cubes without
+    # drill data, like the reference)
+    checks = {}
+    stds = [float(np.std(f["grav"])), float(np.std(f["mag"])), float(np.std(f["drillfield"])) if nd else float("nan")]
+    for i, nm in enumerate(("density", "magsus", "drill")):
+        if i == 2 and not nd:
+            checks["drill_cubes_nan"] = bool(np.isnan(cubes[2]).all() and np.isnan(cubes[5]).all())
+            continue
+        v = np.asarray(cubes[3 + i])
+        checks[nm + "_var_in_prior_bounds"] = bool(np.isfinite(v).all() and v.min() >= -1e-9 * stds[i] ** 2 and v.max() <= (1.0 + 1e-9) * stds[i] ** 2)
+        checks[nm + "_var_reduction_min"] = float(1.0 - v.max() / stds[i] ** 2)
+        checks[nm + "_rec_finite"] = bool(np.isfinite(cubes[i]).all())
+    # BASELINE config 5: "BO acquisition sweep" on the result cubes -- the utility of a vertical drill hole at EVERY voxel column
+    # (run_geobo.py:175-200 for all (x, y) at once, csrc/acq.cu) on rank 0, timed end to end (upload of two cubes, sweep, download)
+    acq = None
+    if args.acq_sweep and rank == 0:
+        from geobo_b200 import acquisition
+        rec = np.nan_to_num(cubes[2] if nd else cubes[0])
+        var = np.nan_to_num(cubes[5] if nd else cubes[3])
+        acquisition.sweep_vertical(rec, var, kappa=1.0, beta=0.1)  # warm-up
+        t0 = time.perf_counter()
+        util, props = acquisition.sweep_vertical(rec, var, kappa=1.0, beta=0.1, top=5)
+        t_acq = time.perf_counter() - t0
+        acq = {"ms": t_acq * 1e3, "columns": int(util.size), "columns_per_s": util.size / t_acq, "best": [[int(a), int(b), float(u)] for a, b, u in props[:3]],
+               "cube": "drill" if nd else "density", "what": "futility_vertical for every voxel column (exhaustive sweep, one launch)"}
 
     if rank != 0:
         return
@@ -444,7 +470,7 @@ def run_ours(args):
                                                              "fft": "block-Toeplitz blocks as zero-padded 3-D FFT convolutions"}[args.structure])) if kron else "dense",
                            "parallelism": "voxel-column shards of Pt x%d" % world, "device_bytes": device_bytes,
                            "inputs": "tests/golden/fullsize_%s.npz (stored synthetic inputs)" % args.workload if fixture is not None else "synth.make_inputs(seed 0)"},
-           "parity": parity,
+           "parity": parity, "checks": checks, "acquisition_sweep": acq,
            "wall_ms_per_step": wall_s * 1e3 / args.steps, "stage_ms": stage_ms, "a_sens_ms": t_sens_ms,
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "roofline": roofline,
            "logl": logl, "info": info_pd, "finite": finite, "gpu": info["name"]}
@@ -558,6 +584,7 @@ def main():
                          "convolutions (any kernel); all reported separately")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--acq-sweep", action="store_true", help="also time the exhaustive vertical-drillhole acquisition sweep on the result cubes (BASELINE config 5)")
     ap.add_argument("--no-fp64-extra", action="store_true", help="skip the one extra step on the fp64 DMMA path (reported under `extra`)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
