@@ -506,7 +506,8 @@ def cpu_baseline(args, cfg, wl, f, y, target_seconds=20.0):
                    "projection (NumPy ufuncs are single-threaded, so the reference's own single process would leave all but one core "
                    "idle for 2/3 of the time), OpenBLAS / LAPACK on %d threads for the rest" % (res["workers"], threads)}
     g = load_fixture(args.workload)
-    if g is not None and "cpu" in g:
+    if g is not None and "cpu" in g and "dgemm_proj" in json.loads(str(g["cpu"])).get("core_seconds_per_stage", {}):
+        # (only for fixtures computed by the DENSE lean path -- the 96x96x48 one went through the Kronecker restatement)
         cf = json.loads(str(g["cpu"]))
         stage_s = cf["wall_s"] - cf["a_sens_s"]           # the metric's stage: everything after the sensitivities
         out["calibration_full_run"] = {"seconds_predict3_stage": stage_s, "worker_processes": cf["workers"], "host_cores": cf["host_cores"],
