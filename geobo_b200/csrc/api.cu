@@ -352,6 +352,12 @@ struct gb_problem {
     int* tile_perm = nullptr;            // [2][6][ceil(ncol / 128)] sorted tile order of the projection kernel + its keys
     int* cull_ext = nullptr;             // [9][2] extents of the non-zero table digits (zero-digit culling of the projection's K steps)
     int a8_slices = 0;
+    // streamed contraction (lean problems whose full-width digit blocks would not fit: 172 GB at 128x128x64): the projection runs
+    // once per column chunk on digit blocks built for that chunk only (a8c) and adds into Pt; the resident digit blocks then cover
+    // only this rank's voxel columns (scope 2: N side of the AkA products)
+    bool stream_a8 = false;
+    uint8_t* a8c[2] = {nullptr, nullptr};
+    int a8c_slices = 0;
     int a8_scope = 0;                    // 0: not built; 1: all N contraction columns (dense projection + AkA); 2: only this rank's voxel
                                          // columns (lean + structured projection: the digits are then only the N side of the AkA products)
     // int8 variance path: explicit Linv, its digit blocks, transposed digit blocks of Pt, per-row-tile column sums of squares
@@ -408,7 +414,7 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     void* ptrs[] = {p->A[0], p->A[1], p->L, p->drill_dev, p->tables, p->Pt, p->tmp, p->Bm, p->ysol, p->ytmp, p->ydev,
-                    p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp, p->cull_ext, p->sync_ctr, p->tile_perm,
+                    p->a8[0], p->a8[1], p->a_exp[0], p->a_exp[1], p->t8, p->t_exp, p->cull_ext, p->sync_ctr, p->tile_perm, p->a8c[0], p->a8c[1],
                     p->Linv, p->tmpL, p->alpha, p->l8, p->l_exp, p->b8, p->b_exp, p->partial,
                     p->edges_dev, p->loc_dev, p->Achunk[0], p->Achunk[1], p->a_amax,
                     p->rf_w, p->rf_z, p->rf_part, p->rf_t, p->vscratch, p->chol_stage, p->chol_pan, p->chol_paninfo, p->kron_f, p->kron_T, p->fft_W, p->fft_tw, p->fft_scratch,
@@ -772,7 +778,14 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
                            "(got zNcube=%lld, columns=%ld); use slices = 0", (long long)p->n[2], ncol);
         // scope of the digit blocks: the dense projection contracts over all N columns; with a structured projection on a lean
         // problem they are only the N side of the AkA products, i.e. this rank's voxel columns (128x128x64: 21 GB instead of 172)
-        const int want_scope = (p->lean && structured) ? 2 : 1;
+        if (p->lean && !structured && p->a8_slices != S) {
+            size_t fr = 0, tot = 0;
+            GB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+            p->stream_a8 = 2 * (size_t)ozaki_rows_bytes(Ns, p->Kp, S, ozaki_tile_np(S)) > tot / 4;
+            if (const char* ev = getenv("GEOBO_B200_STREAM_A8")) p->stream_a8 = atoi(ev) != 0;
+        }
+        const bool streamed = p->lean && !structured && p->stream_a8;
+        const int want_scope = (p->lean && (structured || streamed)) ? 2 : 1;
         if (p->a8_slices != S || (p->a8_scope != want_scope && !(p->a8_scope == 1 && want_scope == 2))) {
             // digit planes of the sensitivities: built once per problem, slice count and scope
             const long a8_kp = want_scope == 2 ? ncp : p->Kp;
@@ -834,6 +847,14 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->b_exp, (size_t)(ldp > 3 * Ns ? ldp : 3 * Ns) * sizeof(int)));
             p->bytes += 2 * (size_t)ozaki_rows_bytes(Ns, a8_kp, S, ozaki_tile_np(S)) + p->b8_bytes;
             p->a8_slices = S;
+        }
+        if (streamed && p->a8c_slices != S) {
+            for (int c = 0; c < 2; ++c) {
+                if (p->a8c[c]) { gb_dev_free(ctx, p->a8c[c]); p->a8c[c] = nullptr; }
+                GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->a8c[c], (size_t)ozaki_rows_bytes(Ns, p->chunk_ld, S, ozaki_tile_np(S))));
+                p->bytes += (size_t)ozaki_rows_bytes(Ns, p->chunk_ld, S, ozaki_tile_np(S));
+            }
+            p->a8c_slices = S;
         }
     }
     if (structured) {
@@ -898,7 +919,41 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             const int nt_ = ozaki_tile_np(S);
             p->ksteps_total = 2.0 * nrp * (double)((Ns + nt_ - 1) / nt_) * (double)((ncol + 127) / 128) * (double)(p->Kp / 32);
         }
-        GB_CUDA(ctx, ozaki_project(oa, S, ctx->sm_count, s));
+        oa.ks_base = 0; oa.cy0 = 0; oa.cy1 = 0; oa.accumulate = 0;
+        if (!(p->lean && p->stream_a8)) {
+            GB_CUDA(ctx, ozaki_project(oa, S, ctx->sm_count, s));
+        } else {
+            // streamed contraction: Pt = sum over column chunks of (digits of the chunk's columns) . (covariance rows of the chunk)
+            int eymax = (int)p->n[1];
+            if (cull) {        // chunks further than the largest y extent from every voxel row of the shard hold only skipped steps
+                int ext_h[18];
+                GB_CUDA(ctx, cudaMemcpyAsync(ext_h, p->cull_ext, sizeof ext_h, cudaMemcpyDeviceToHost, s));
+                GB_CUDA(ctx, cudaStreamSynchronize(s));
+                eymax = 0;
+                for (int c = 0; c < 2; ++c)
+                    for (int r = 0; r < nrp; ++r) eymax = std::max(eymax, ext_h[2 * (c * 3 + r)]);
+            }
+            const int64_t XZ = p->n[0] * p->n[2];
+            const int64_t sy0 = p->c0 / XZ, sy1 = (p->c1 - 1) / XZ;
+            GB_CUDA(ctx, cudaMemsetAsync(p->Pt, 0, (size_t)2 * Ns * ldp * sizeof(double), s));
+            GB_TRY(lean_for_each_chunk(p, [&](int64_t j0, int64_t ncols) -> cudaError_t {
+                const int64_t y0 = j0 / XZ, y1 = (j0 + ncols) / XZ;
+                if (y1 <= sy0 - eymax || y0 > sy1 + eymax) return cudaSuccess;
+                for (int c = 0; c < 2; ++c) {
+                    cudaError_t e = ozaki_slice_rows_range(p->Achunk[c], Ns, ncols, p->chunk_ld, S, p->a_exp[c], p->a8c[c], round_up(ncols, 32),
+                                                           ozaki_tile_np(S), 0, s);
+                    if (e != cudaSuccess) return e;
+                }
+                OzakiArgs ob = oa;
+                ob.a8[0] = p->a8c[0]; ob.a8[1] = p->a8c[1];
+                ob.kp = round_up(ncols, 32);
+                ob.ks_base = (int)(j0 / 32); ob.cy0 = (int)y0; ob.cy1 = (int)y1; ob.accumulate = 1;
+                cudaError_t e = cudaMemsetAsync(p->sync_ctr, 0, sizeof(unsigned int), s);
+                if (e != cudaSuccess) return e;
+                p->nlaunch += 3;
+                return ozaki_project(ob, S, ctx->sm_count, s);
+            }));
+        }
         p->nlaunch += 2;                  // table slicing (absmax + digits)
     } else {
         gemm::TaskBatch b;

@@ -143,6 +143,7 @@ struct OzakiArgs {
     const int* cull;         // [9][2] device: extents (|dy|, |dx|) of the non-zero digits of every table (ozaki_table_extents), or null
     int n[3];                // xN, yN, zN
     unsigned long long* steps_ctr;   // device counter, ZERO at launch: K steps visited (sum over tiles); or null
+    int ks_base, cy0, cy1, accumulate;   // streamed contraction (see ozaki::Params); all 0 for a launch over the whole contraction
     int sync_slack;          // rounds of slack of the pacing (0 = strict)
     int* perm_scratch;       // [2][6][ceil(ncol / 128)] ints (tile order sorted by K-step count + keys), or null = natural tile order
     unsigned int* sync_ctr;  // device counter, ZERO at launch: tile-round pacing of the copy lanes (keeps the shared K strips in L2); or null

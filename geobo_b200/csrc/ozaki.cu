@@ -151,6 +151,10 @@ struct Params {
     // the copy lanes count arrivals in this device counter and start a round's loads together.  null = no pacing.
     unsigned int* sync_ctr;
     int sync_slack;                  // rounds a CTA may run ahead of the slowest one (0: all start a round together)
+    // streamed contraction: this launch covers only the contraction voxels of the voxel rows [cy0, cy1) (cy1 <= cy0: all rows);
+    // a8 then holds the digit blocks of just those columns, its first K step being step ks_base of the cube, and the result
+    // is added to Pt (accumulate != 0) instead of replacing it
+    int ks_base, cy0, cy1, accumulate;
     // tile order: with culling the tiles of one round have different numbers of K steps (cube edges), and paced CTAs would wait
     // for the longest one.  perm[tq * n_itile + pos] = voxel-column tile handled at position pos of task tq, sorted by decreasing
     // step count, so that the (up to) gridDim.x tiles of a round cost the same.  null = natural order.
@@ -175,7 +179,7 @@ __device__ __forceinline__ KRange tile_krange(const Params& P, int task, int iti
     KRange r;
     const int XZ = P.xN * P.zN;
     if (P.cull == nullptr || (XZ & 31) != 0) {
-        r.jya = 0; r.nrows = 1; r.koff = 0; r.w = ksteps; r.rowsteps = 0; r.nt = (uint32_t)ksteps;
+        r.jya = 0; r.nrows = 1; r.koff = P.ks_base; r.w = ksteps; r.rowsteps = 0; r.nt = (uint32_t)ksteps;
         return r;
     }
     const int ey = P.cull[2 * task], ex = P.cull[2 * task + 1];
@@ -184,8 +188,10 @@ __device__ __forceinline__ KRange tile_krange(const Params& P, int task, int iti
     const int iya = (int)(g0 / XZ), iyb = (int)(g1 / XZ);
     int ixa = 0, ixb = P.xN - 1;
     if (iya == iyb) { ixa = (int)(g0 % XZ) / P.zN; ixb = (int)(g1 % XZ) / P.zN; }
-    const int jya = max(0, iya - ey), jyb = min(P.yN - 1, iyb + ey);
+    int jya = max(0, iya - ey), jyb = min(P.yN - 1, iyb + ey);
+    if (P.cy1 > P.cy0) { jya = max(jya, P.cy0); jyb = min(jyb, P.cy1 - 1); }       // streamed contraction: rows of this launch only
     const int jxa = max(0, ixa - ex), jxb = min(P.xN - 1, ixb + ex);
+    if (jyb < jya) { r.jya = 0; r.nrows = 0; r.koff = 0; r.w = 1; r.rowsteps = 0; r.nt = 0; return r; }
     r.rowsteps = XZ / 32;
     r.jya = jya;
     r.nrows = jyb - jya + 1;
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
                     for (int q = 0; q < S; ++q) word[kh][q] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)q * plane));
                 }
             };
-            {
+            if (nt > 0) {
                 lj_t = ks;
                 lj_row = ks / kr.w;                 // one division per tile
                 lj_q = ks - lj_row * kr.w;
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
                 const KRange kr = tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, tile_at(P, tq, (int)((tile % tiles_per_task) % P.n_itile)), ksteps);
                 if (P.steps_ctr) atomicAdd(P.steps_ctr, (unsigned long long)kr.nt);
                 for (int jj = 0; jj < kr.nrows; ++jj) {
-                    const uint8_t* rowsrc = src + (size_t)((kr.jya + jj) * kr.rowsteps + kr.koff) * B_BYTES;
+                    const uint8_t* rowsrc = src + (size_t)((kr.jya + jj) * kr.rowsteps + kr.koff - P.ks_base) * B_BYTES;
                     for (int q = 0; q < kr.w; ++q, ++it) {
                         const int st = (int)(it % SB);
                         mbar_wait(&done_bar[st], ((it / SB) & 1) ^ 1);
@@ -492,7 +498,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
                                 for (int lvl = 1; lvl < S; ++lvl) acc = acc * 256 + (long long)(int)v[lvl][k];
                                 const double add = ldexp((double)acc, aexp[s] + ebase);
                                 double* dst = pcol + (long)(n0 + k) * P.ldp;          // 32 lanes -> 32 consecutive doubles of one Pt row
-                                *dst = (k0 == 0) ? add : *dst + add;
+                                *dst = (k0 == 0 && !P.accumulate) ? add : *dst + add;
                             }
                         }
                     }
@@ -639,6 +645,7 @@ cudaError_t ozaki_project(const OzakiArgs& a, int slices, int sm_count, cudaStre
     P.sync_ctr = a.sync_ctr;
     P.sync_slack = a.sync_slack;
     P.perm = nullptr;
+    P.ks_base = a.ks_base; P.cy0 = a.cy0; P.cy1 = a.cy1; P.accumulate = a.accumulate;
     P.steps_ctr = a.steps_ctr;
     P.xN = a.n[0]; P.yN = a.n[1]; P.zN = a.n[2];
     P.chunk = ozaki_chunk();

@@ -108,6 +108,16 @@ def test_lean_mode_regenerated_sensitivities_match_resident_ones(ctx, monkeypatc
         ref, ex = o.cubing_lean(c, f["grav"], f["mag"], f["drillfield"], f["sensor_locations"], f["drilldata0"], gp_length=gl.copy())
     for n, a, r in zip(CUBES, out1, ref):
         assert normwise_err(a, r) < 1e-6, n
+    # streamed contraction (GEOBO_B200_STREAM_A8=1: the full-width digit blocks are never resident either -- 172 GB at 128x128x64):
+    # one projection launch per column chunk on digits built for that chunk, added into Pt; with and without culling
+    monkeypatch.setenv("GEOBO_B200_STREAM_A8", "1")
+    for cull in ("1", "0"):
+        monkeypatch.setenv("GEOBO_B200_CULL", cull)
+        inv_s, out_s = run_cubing(f, gl=gl.copy())
+        for n, a, b in zip(CUBES, out_s, out1):
+            assert normwise_err(a, b) < 1e-9, (n, cull)           # same digits; only the order of the fp64 flush sums changes
+    monkeypatch.delenv("GEOBO_B200_CULL")
+    monkeypatch.setenv("GEOBO_B200_STREAM_A8", "0")
     # structured projections on a lean problem: the rows are regenerated in sensor-row chunks (7 rows here: ragged), and only the
     # digits of this rank's voxel columns are kept (N side of the AkA products)
     structure = {"exp": "kron", "sparse": "compact", "matern32": "fft"}[kf]
