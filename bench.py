@@ -292,7 +292,7 @@ def run_ours(args):
     inv.create_cubegeometry()
     inv.gp_length = inv.gp_length * np.asarray(wl.get("gl_mult", (1.0, 1.0, 1.0)))
     gl_eff = effective_lengths(config_loader, wl)
-    c0, c1 = dist.shard_columns(N, world, rank) if world > 1 else (0, N)
+    c0, c1 = inv.shard_bounds()[rank] if world > 1 else (0, N)      # balanced by estimated work per voxel column (culling)
     drill_idx = np.flatnonzero(f["drilldata0"].ravel() != 0)
     prob = _lib.Problem(ctx, (xN, yN, zN), (config_loader.xvoxsize, config_loader.yvoxsize, config_loader.zvoxsize),
                         inv.Edges, f["sensor_locations"], config_loader.magneticField, config_loader.c_MILLIGALS_UNITS,

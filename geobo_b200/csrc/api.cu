@@ -444,12 +444,14 @@ static cudaError_t sens_generate(gb_problem* p, int y0, int y1, double* out_g, d
 }
 
 // lean mode: f(j0, ncols) for every column chunk, with the chunk's columns [j0, j0 + ncols) regenerated in p->Achunk[0 / 1]
+// (only the chunks that intersect the columns [ja, jb) when that range is given)
 template <typename F>
-static int lean_for_each_chunk(gb_problem* p, F f) {
+static int lean_for_each_chunk(gb_problem* p, F f, int64_t ja = 0, int64_t jb = -1) {
     gb_ctx* ctx = p->ctx;
     const int64_t XZ = p->n[0] * p->n[2], yN = p->n[1];
     for (int64_t y0 = 0; y0 < yN; y0 += p->chunk_y) {
         const int64_t y1 = std::min<int64_t>(yN, y0 + p->chunk_y);
+        if (jb >= 0 && (y1 * XZ <= ja || y0 * XZ >= jb)) continue;
         GB_CUDA(ctx, sens_generate(p, (int)y0, (int)y1, p->Achunk[0], p->Achunk[1], p->chunk_ld));
         p->nlaunch += 2;
         GB_CUDA(ctx, f(y0 * XZ, (y1 - y0) * XZ));
@@ -1104,10 +1106,21 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             if (!p->lean) {
                 GB_CUDA(ctx, refine_at_alpha(ra, p->alpha, p->rf_w, s));   // w = A3^T alpha
             } else {
+                // every rank regenerates only the chunks of its own voxel columns; the other entries of w = A3^T alpha come from the
+                // other ranks through one all-reduce (each entry has exactly one non-zero contribution: exact in any order)
+                if (ctx->nranks > 1) GB_CUDA(ctx, cudaMemsetAsync(ra.partial, 0, (size_t)16 * p->Kp * sizeof(double), s));
                 GB_TRY(lean_for_each_chunk(p, [&](int64_t j0, int64_t ncols) -> cudaError_t {
-                    return refine_at_alpha_chunk(ra, p->Achunk[0], p->Achunk[1], p->chunk_ld, j0, ncols, p->alpha, s);
-                }));
+                    const int64_t a0 = ctx->nranks > 1 ? std::max<int64_t>(j0, p->c0) : j0;
+                    const int64_t a1 = ctx->nranks > 1 ? std::min<int64_t>(j0 + ncols, p->c1) : j0 + ncols;
+                    if (a1 <= a0) return cudaSuccess;
+                    return refine_at_alpha_chunk(ra, p->Achunk[0] + (a0 - j0), p->Achunk[1] + (a0 - j0), p->chunk_ld, a0, a1 - a0, p->alpha, s);
+                }, ctx->nranks > 1 ? p->c0 : 0, ctx->nranks > 1 ? p->c1 : -1));
                 GB_CUDA(ctx, refine_at_alpha_finish(ra, p->alpha, p->rf_w, s));
+                if (ctx->nranks > 1) {
+                    if (p->nd) GB_CUDA(ctx, cudaMemsetAsync(p->rf_w + 2 * p->Kp, 0, (size_t)p->Kp * sizeof(double), s));   // the drill block is scattered below
+                    GB_TRY(comm_allreduce_sum_f64(ctx, p->rf_w, (size_t)2 * p->Kp));
+                    if (p->nd) GB_CUDA(ctx, refine_at_alpha_finish_drill(ra, p->alpha, p->rf_w, s));
+                }
             }
             if (structured) {                                              // z = K w   (this rank's voxel columns)
                 for (int c = 0; c < nrp; ++c)                              // fixed order c = 0, 1, 2: deterministic sums (c = 2: zero weights without drill data)
@@ -1128,7 +1141,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
                     cudaError_t e = refine_a_z_chunk(ra, p->Achunk[0], p->Achunk[1], p->chunk_ld, j0, ja, jb, p->rf_z, rt, first ? 0 : 1, s);
                     first = false;
                     return e;
-                }));
+                }, p->c0, p->c1));
                 GB_CUDA(ctx, refine_a_z_drill(ra, p->rf_z, rt, s));
             }
             GB_TRY(comm_allreduce_sum_f64(ctx, rt, (size_t)Mp));

@@ -198,6 +198,7 @@ cudaError_t refine_at_alpha(const RefineArgs& a, const double* alpha, double* w 
 cudaError_t refine_at_alpha_chunk(const RefineArgs& a, const double* A0, const double* A1, long ld, long j0, long ncols, const double* alpha,
                                   cudaStream_t s);
 cudaError_t refine_at_alpha_finish(const RefineArgs& a, const double* alpha, double* w, cudaStream_t s);
+cudaError_t refine_at_alpha_finish_drill(const RefineArgs& a, const double* alpha, double* w, cudaStream_t s);
 // t (+)= A_c[:, ja : jb) z[c][ja - c0 : jb - c0)  for a column chunk held at A0 / A1 (column ja of the cube = column ja - j0 of the chunk)
 cudaError_t refine_a_z_chunk(const RefineArgs& a, const double* A0, const double* A1, long ld, long j0, long ja, long jb, const double* z,
                              double* t, int accumulate, cudaStream_t s);

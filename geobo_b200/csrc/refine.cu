@@ -306,6 +306,12 @@ cudaError_t refine_at_alpha_chunk(const RefineArgs& a, const double* A0, const d
     return cudaGetLastError();
 }
 
+// w[2][drill] = alpha_drill (after an all-reduce of the two survey blocks of w, which must not sum the replicated drill block)
+cudaError_t refine_at_alpha_finish_drill(const RefineArgs& a, const double* alpha, double* w, cudaStream_t s) {
+    if (a.nd) w_drill_kernel<<<(unsigned)((a.nd + 255) / 256), 256, 0, s>>>(alpha + 2 * a.Ns, a.drill, a.nd, w + 2 * a.Kp);
+    return cudaGetLastError();
+}
+
 cudaError_t refine_at_alpha_finish(const RefineArgs& a, const double* alpha, double* w, cudaStream_t s) {
     w_reduce_kernel<<<(unsigned)((a.Kp + 255) / 256), 256, 0, s>>>(a.partial, a.nsplit, a.Kp, a.N, w);
     if (a.nd) w_drill_kernel<<<(unsigned)((a.nd + 255) / 256), 256, 0, s>>>(alpha + 2 * a.Ns, a.drill, a.nd, w + 2 * a.Kp);

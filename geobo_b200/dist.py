@@ -41,6 +41,33 @@ def shard_columns(n_vox, world, rank, align=128):
     return c0, c1
 
 
+def shard_bounds(n_vox, world, weights=None, align=128):
+    """Contiguous voxel-column shards [(c0, c1)] for all ranks.  ``weights`` (one non-negative number per equal-sized block of
+    columns, e.g. per voxel row of the cube) balances the CUMULATIVE WEIGHT instead of the column count: with zero-digit culling
+    the projection work of a voxel column depends on how many voxel rows lie inside the covariance's reach, so the ranks that own
+    the cube's edge rows would otherwise finish early and wait in the AkA all-reduce.  Boundaries are multiples of ``align``; every
+    rank owns at least ``align`` columns.  ``weights=None``: the uniform split of ``shard_columns``."""
+    if weights is None or world == 1:
+        return [shard_columns(n_vox, world, r, align) for r in range(world)]
+    w = np.asarray(weights, dtype=float)
+    if w.ndim != 1 or w.size < 1 or (w < 0).any() or not w.sum() > 0:
+        raise ValueError("weights must be a non-empty vector of non-negative numbers")
+    if n_vox < world * align:
+        raise ValueError("cube with %d voxels is too small to shard over %d ranks at alignment %d" % (n_vox, world, align))
+    # cumulative weight as a piecewise-linear function of the column index
+    edges = np.linspace(0.0, float(n_vox), w.size + 1)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for k in range(1, world):
+        c = float(np.interp(k * cum[-1] / world, cum, edges))
+        c = int(round(c / align)) * align
+        c = max(c, cuts[-1] + align)                       # at least one aligned block per rank ...
+        c = min(c, n_vox - (world - k) * align)            # ... also for the ranks still to come
+        cuts.append(c)
+    cuts.append(n_vox)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 # ------------------------------------------------------------------ TCP control plane (rank 0 = hub)
 def _send(sock, obj):
     data = pickle.dumps(obj, protocol=4)
@@ -184,16 +211,19 @@ def max_over_ranks(value):
     return float(max(_allgather_obj(float(value))))
 
 
-def allgather_columns(local, n_vox, align=128, ctx=None):
+def allgather_columns(local, n_vox, align=128, ctx=None, bounds=None):
     """``local``: (k, ncol_local) array of this rank's voxel columns -> (k, n_vox) on every rank.
     With a ``_lib.Context`` that has an NCCL communicator the gather runs over NCCL/NVLink inside the library
-    (``gb_comm_allgather``); otherwise over the host control plane."""
+    (``gb_comm_allgather``); otherwise over the host control plane.  ``bounds``: the shards of all ranks (``shard_bounds``) when
+    they are not the uniform split."""
     world, rk = _state["world"], _state["rank"]
     local = np.ascontiguousarray(local, dtype=np.float64)
     if world <= 1:
         return local
     k = local.shape[0]
-    per = shard_columns(n_vox, world, 0, align)[1]
+    if bounds is None:
+        bounds = [shard_columns(n_vox, world, r, align) for r in range(world)]
+    per = max(c1 - c0 for c0, c1 in bounds)
     if ctx is not None and getattr(ctx, "nranks", 1) == world:
         buf = np.zeros((k, per))
         buf[:, :local.shape[1]] = local
@@ -202,6 +232,6 @@ def allgather_columns(local, n_vox, align=128, ctx=None):
         outs = _allgather_obj(local)
     full = np.empty((k, n_vox))
     for r in range(world):
-        c0, c1 = shard_columns(n_vox, world, r, align)
+        c0, c1 = bounds[r]
         full[:, c0:c1] = outs[r][:, :c1 - c0]
     return full

@@ -125,6 +125,42 @@ class Inversion:
                                   self.gp_amp if gp_amp is None else gp_amp, _cfg.kernelfunc, self._slices(),
                                   int(getattr(_cfg, "refine", 1)), self._structure())
 
+    def _culling_reach_rows(self, slices):
+        """Voxel rows beyond which every digit of the covariance tables is zero for the int8 path with ``slices`` digits (an
+        estimate for load balancing only -- the kernel takes the exact extents from the digit tables): the blocks' values along
+        the y axis, evaluated on the device, against the last-digit threshold 2^-(8 slices) of the block's maximum."""
+        gl = np.array(self.gp_length, dtype=float).copy()
+        kernel.dedup_lengthscales(gl)
+        yN = int(_cfg.yNcube)
+        d2 = (np.arange(yN, dtype=float) * _cfg.yvoxsize) ** 2
+        ctx = _lib.default_context()
+        reach = 0
+        with np.errstate(all="ignore"):
+            for c in range(2):
+                for r in range(3):
+                    v = np.abs(ctx.cov_function(_cfg.kernelfunc, int(c != r), d2, gl[c], gl[r] if c != r else 0.0))
+                    v = np.nan_to_num(v, nan=0.0, posinf=0.0)
+                    if v.max() > 0:
+                        nz = np.flatnonzero(v >= v.max() * 2.0 ** (-8 * slices))
+                        reach = max(reach, int(nz.max()) if nz.size else 0)
+        return reach
+
+    def shard_bounds(self):
+        """Voxel-column shards of all ranks.  On the tensor-core path they balance the estimated work per voxel column -- the
+        projection visits only the voxel rows inside the covariance's reach (zero-digit culling), fewer for the cube's edge rows;
+        the triangular-solve / variance stages cost the same for every column -- instead of the column count."""
+        xN, yN, zN = _cfg.xNcube, _cfg.yNcube, _cfg.zNcube
+        N, world = xN * yN * zN, _dist.world_size()
+        slices = self._slices()
+        if world <= 1 or not slices or self._structure() != "dense":
+            return _dist.shard_bounds(N, world)
+        reach = self._culling_reach_rows(slices)
+        iy = np.arange(yN)
+        nrows = np.minimum(yN - 1, iy + reach) - np.maximum(0, iy - reach) + 1
+        share = float(getattr(_cfg, "shard_projection_share", 0.75))     # share of the projection in the per-column cost
+        w = share * nrows / nrows.max() + (1.0 - share)
+        return _dist.shard_bounds(N, world, weights=w)
+
     def _build_problem(self):
         if not hasattr(self, "Edges"):
             self.create_cubegeometry()
@@ -139,7 +175,8 @@ class Inversion:
             raise IndexError("sensor_locations has %d rows; the forward model needs xNcube*yNcube=%d" % (loc.shape[0], nsens))
         ctx = _lib.default_context()
         world, rk = _dist.world_size(), _dist.rank()
-        c0, c1 = _dist.shard_columns(N, world, rk) if world > 1 else (0, N)
+        self._bounds = self.shard_bounds() if world > 1 else [(0, N)]
+        c0, c1 = self._bounds[rk]
         if self._problem is not None:
             self._problem.close()
         self._problem = _lib.Problem(ctx, (xN, yN, zN), (_cfg.xvoxsize, _cfg.yvoxsize, _cfg.zvoxsize), self.Edges,
@@ -164,7 +201,7 @@ class Inversion:
             sys.exit(1)
         N = self._problem.N
         if _dist.world_size() > 1:
-            both = _dist.allgather_columns(np.vstack([mu, var]), N, ctx=self._problem.ctx)
+            both = _dist.allgather_columns(np.vstack([mu, var]), N, ctx=self._problem.ctx, bounds=self._bounds)
             mu, var = both[:3], both[3:]
         self._lazy = {}
         mu = np.ascontiguousarray(mu).reshape(3 * N)

@@ -91,6 +91,29 @@ def test_shard_columns_partition():
         shard_columns(200, 4, 3)
 
 
+def test_shard_bounds_balance_the_cumulative_weight():
+    """Weighted contiguous shards (culled projection work per voxel row): aligned, exhaustive, every rank non-empty, and the edge
+    ranks -- whose rows see fewer rows inside the covariance's reach -- get more columns."""
+    from geobo_b200.dist import shard_bounds, shard_columns
+    assert shard_bounds(6400, 3) == [shard_columns(6400, 3, r) for r in range(3)]
+    yN, XZ, reach = 96, 96 * 48, 23
+    iy = np.arange(yN)
+    nrows = np.minimum(yN - 1, iy + reach) - np.maximum(0, iy - reach) + 1
+    w = 0.75 * nrows / nrows.max() + 0.25
+    col_w = np.repeat(w, XZ)
+    for world in (2, 3, 4, 8):
+        b = shard_bounds(yN * XZ, world, weights=w)
+        assert b[0][0] == 0 and b[-1][1] == yN * XZ and all(a[1] == c[0] for a, c in zip(b, b[1:]))
+        assert all(c0 % 128 == 0 and c1 > c0 for c0, c1 in b)
+        loads = np.array([col_w[c0:c1].sum() for c0, c1 in b])
+        assert loads.max() / loads.min() < 1.02
+        if world >= 4:
+            assert b[0][1] - b[0][0] > b[1][1] - b[1][0]
+    assert shard_bounds(512, 4, weights=[100, 1, 1, 1]) == [(0, 128), (128, 256), (256, 384), (384, 512)]   # never an empty rank
+    with pytest.raises(ValueError):
+        shard_bounds(256, 4, weights=[1, 1])
+
+
 def _worker(rank, world, port, q):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
