@@ -158,8 +158,22 @@ class Inversion:
         iy = np.arange(yN)
         nrows = np.minimum(yN - 1, iy + reach) - np.maximum(0, iy - reach) + 1
         share = float(getattr(_cfg, "shard_projection_share", 0.75))     # share of the projection in the per-column cost
-        w = share * nrows / nrows.max() + (1.0 - share)
-        return _dist.shard_bounds(N, world, weights=w)
+        # the ranks that own edge rows get more columns, i.e. a larger slice of Pt: keep the largest shard inside the device memory
+        # (rough per-column / fixed byte counts of the tensor-core path), falling back towards the uniform split
+        Ns = xN * yN
+        nd = int(np.count_nonzero(np.asarray(self.drilldata0))) if hasattr(self, "drilldata0") else 0
+        Mp = -(-(2 * Ns + nd) // 128) * 128
+        per_col = Mp * (3 if nd else 2) * 8.0 + 2.0 * slices * Ns
+        fixed = 2.0 * Mp * Mp * 8.0 + 14e9
+        total = float(_lib.default_context().device_info()["total_bytes"])
+        bounds = _dist.shard_bounds(N, world)
+        for sh in (share, 0.5 * share, 0.25 * share):
+            w = sh * nrows / nrows.max() + (1.0 - sh)
+            cand = _dist.shard_bounds(N, world, weights=w)
+            if max(c1 - c0 for c0, c1 in cand) * per_col + fixed < 0.85 * total:
+                bounds = cand
+                break
+        return bounds
 
     def _build_problem(self):
         if not hasattr(self, "Edges"):
