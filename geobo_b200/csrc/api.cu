@@ -431,6 +431,16 @@ extern "C" int gb_problem_destroy(gb_problem* p) {
 
 extern "C" uint64_t gb_problem_device_bytes(gb_problem* p) { return p ? p->bytes : 0; }
 
+// GEOBO_B200_MEMLOG=1: free / total device memory at the allocation milestones, on stderr
+static void memlog(gb_problem* p, const char* what) {
+    static int on = -1;
+    if (on < 0) { const char* ev = getenv("GEOBO_B200_MEMLOG"); on = ev && atoi(ev) != 0; }
+    if (!on) return;
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    fprintf(stderr, "[geobo_b200 rank %d] %-28s free %.2f GB of %.2f GB, problem buffers %.2f GB\n", p->ctx->rank, what, fr / 1e9, tot / 1e9, p->bytes / 1e9);
+}
+
 // both sensitivity matrices for the voxel rows [y0, y1): out_c[s * ld + (j - y0 xN zN)]   (inversion.py:223-224; gravity is called
 // with magneticField * 0)
 static cudaError_t sens_generate(gb_problem* p, int y0, int y1, double* out_g, double* out_m, int64_t ld) {
@@ -542,7 +552,7 @@ extern "C" int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* d, gb_probl
     PCUDA(dev_alloc(p, &p->drill_dev, (size_t)p->nd + 1, false));
     PCUDA(dev_alloc(p, &p->tables, (size_t)9 * p->ext, false));
     PCUDA(dev_alloc(p, &p->Pt, (size_t)p->Mp * p->ldp, true));
-    PCUDA(dev_alloc(p, &p->tmp, (size_t)128 * p->ldp, true));
+    if (!p->lean) PCUDA(dev_alloc(p, &p->tmp, (size_t)128 * p->ldp, true));      // row-block scratch of the fp64 solve (lean problems never run it)
     PCUDA(dev_alloc(p, &p->Bm, (size_t)p->Mp * p->Mp, true));
     PCUDA(dev_alloc(p, &p->ysol, (size_t)p->Mp * 16, true));
     PCUDA(dev_alloc(p, &p->ytmp, (size_t)128 * 16, true));
@@ -580,6 +590,7 @@ extern "C" int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* d, gb_probl
         p->ms[GB_T_SENS] = t;
     }
 #undef PCUDA
+    memlog(p, "problem created");
     *out = p;
     return GB_OK;
 }
@@ -841,7 +852,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             // min(all of Pt, GEOBO_B200_B8_MB, default 12 GB) -- the variance product walks Pt in column chunks of that size
             const size_t aka_bytes = (size_t)ozaki_rows_bytes(Ns, ncp, S, 128);
             const size_t var_all = (size_t)ozaki_cols_bytes(ldp, Mp, S);
-            size_t var_budget = (size_t)12288 << 20;
+            size_t var_budget = (size_t)(p->lean ? 8192 : 12288) << 20;      // lean problems are the memory-tight ones
             if (const char* ev = getenv("GEOBO_B200_B8_MB")) var_budget = (size_t)(atol(ev) > 0 ? atol(ev) : 12288) << 20;
             const size_t var_bytes = var_all < var_budget ? var_all : var_budget;
             p->b8_bytes = aka_bytes > var_bytes ? aka_bytes : var_bytes;
@@ -849,6 +860,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->b_exp, (size_t)(ldp > 3 * Ns ? ldp : 3 * Ns) * sizeof(int)));
             p->bytes += 2 * (size_t)ozaki_rows_bytes(Ns, a8_kp, S, ozaki_tile_np(S)) + p->b8_bytes;
             p->a8_slices = S;
+            memlog(p, "digit blocks + scratch");
         }
         if (streamed && p->a8c_slices != S) {
             for (int c = 0; c < 2; ++c) {
@@ -1071,6 +1083,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
             if (ozaki_colsumsq_scratch_bytes((int)Mp, S, ctx->sm_count))
                 GB_CUDA(ctx, gb_dev_malloc(ctx, (void**)&p->vscratch, (size_t)ozaki_colsumsq_scratch_bytes((int)Mp, S, ctx->sm_count)));
             p->var_slices = S;
+            memlog(p, "variance-stage buffers");
         }
         // Two buffers of this stage live inside others whose contents are dead by then (at 128x128x64 they would be 8.7 + 5.4 GB):
         //  * the Mp x Mp scratch of the triangular inverse sits in the digit scratch b8 (idle between the AkA products and the

@@ -163,9 +163,9 @@ class Inversion:
         Ns = xN * yN
         nd = int(np.count_nonzero(np.asarray(self.drilldata0))) if hasattr(self, "drilldata0") else 0
         Mp = -(-(2 * Ns + nd) // 128) * 128
-        per_col = Mp * (3 if nd else 2) * 8.0 + 2.0 * slices * Ns
-        fixed = 2.0 * Mp * Mp * 8.0 + 14e9
-        total = float(_lib.default_context().device_info()["total_bytes"])
+        per_col = Mp * (3 if nd else 2) * 8.0 + 3.0 * slices * Ns         # Pt, shard digit blocks, row digits of one AkA block
+        fixed = 2.0 * Mp * Mp * 8.0 + 20e9                                # AkA / L and Linv; digit scratch, chunk buffers, tables, NCCL
+        total = float(_lib.default_context().device_info()["free_bytes"]) / 0.85     # (what is free now, after context + NCCL set-up)
         bounds = _dist.shard_bounds(N, world)
         for sh in (share, 0.5 * share, 0.25 * share):
             w = sh * nrows / nrows.max() + (1.0 - sh)
