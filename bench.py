@@ -487,7 +487,7 @@ def ctx_device():
     return int(os.environ.get("GEOBO_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
 
 
-def cpu_baseline(args, cfg, wl, f, y, target_seconds=20.0):
+def cpu_baseline(args, cfg, wl, f, y, target_seconds=20.0, pool=None, probe_seconds=None):
     """Lean NumPy/SciPy restatement of the reference (oracle/numpy_oracle.py) on this box's host cores: the projection in one
     worker process per core (the arrangement of the full-size fixture runs), the other stages with BLAS on all threads."""
     from oracle import numpy_oracle as o
@@ -498,11 +498,12 @@ def cpu_baseline(args, cfg, wl, f, y, target_seconds=20.0):
     gl = c.gp_lengthscale * c.xvoxsize * np.asarray(wl.get("gl_mult", (1.0, 1.0, 1.0)))
     # the sensitivities only enter the timed stages as dgemm operands (timing is value-independent): the oracle's A_sens for a
     # few sensors, tiled (oracle.TiledSens) -- the bounded sample does not spend minutes in the (untimed) A_sens loop
-    res = o.cpu_baseline_sample(cfg, didx, np.nan_to_num(y), gp_length=gl.copy(), target_seconds=target_seconds, workers=threads)
+    res = o.cpu_baseline_sample(cfg, didx, np.nan_to_num(y), gp_length=gl.copy(), target_seconds=target_seconds, workers=threads, pool=pool,
+                                probe_seconds=probe_seconds)
     out = {"value": N / res["seconds_estimated"], "unit": "voxels/s", "cores": int(threads), "kind": "port",
            "host_cpus": os.cpu_count(), "sample": res["sample"], "full_inversion": bool(res["full"]),
            "seconds_estimated_full": res["seconds_estimated"], "seconds_measured": res["seconds_measured"], "stages_s": res["stages"],
-           "pair_seconds": res["pair_seconds"],
+           "pair_seconds": res["pair_seconds"], "probe_seconds": res["probe_seconds"],
            "what": "oracle/numpy_oracle.py lean restatement of geobo predict3; every host core busy: %d worker processes for the "
                    "projection (NumPy ufuncs are single-threaded, so the reference's own single process would leave all but one core "
                    "idle for 2/3 of the time), OpenBLAS / LAPACK on %d threads for the rest" % (res["workers"], threads)}
@@ -548,10 +549,14 @@ def run_reference(args):
         y = rng.standard_normal(2 * Ns + nd)
     per_step_budget = max(5.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
     vals, last = [], None
-    for i in range(args.warmup + args.steps):
-        last = cpu_baseline(args, cfg, wl, f, y, target_seconds=per_step_budget)
-        if i >= args.warmup:
-            vals.append(last["value"])
+    import multiprocessing as mp
+    # one worker pool and one probe for all steps (process start-up is not part of a step)
+    with mp.get_context("spawn").Pool(cpu_threads()) as pool:
+        for i in range(args.warmup + args.steps):
+            last = cpu_baseline(args, cfg, wl, f, y, target_seconds=per_step_budget, pool=pool,
+                                probe_seconds=None if last is None else last["probe_seconds"])
+            if i >= args.warmup:
+                vals.append(last["value"])
     value = float(np.mean(vals))
     cb = {k: last[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus", "full_inversion", "pair_seconds") if k in last}
     cb["value"] = value

@@ -165,7 +165,10 @@ class Inversion:
         Mp = -(-(2 * Ns + nd) // 128) * 128
         per_col = Mp * (3 if nd else 2) * 8.0 + 3.0 * slices * Ns         # Pt, shard digit blocks, row digits of one AkA block
         fixed = 2.0 * Mp * Mp * 8.0 + 20e9                                # AkA / L and Linv; digit scratch, chunk buffers, tables, NCCL
-        total = float(_lib.default_context().device_info()["free_bytes"]) / 0.85     # (what is free now, after context + NCCL set-up)
+        # what is free now (after context + NCCL set-up, incl. what the context's buffer cache would give back), with a margin:
+        # at 128x128x64 on 8 GPUs the first weighted split left 0.24 GB free on the edge ranks (profiles/r2_memlog_cfg5_dense_n8_rank0.txt)
+        info = _lib.default_context().device_info()
+        total = (0.9 * float(info["free_bytes"]) - 6e9) / 0.85
         bounds = _dist.shard_bounds(N, world)
         for sh in (share, 0.5 * share, 0.25 * share):
             w = sh * nrows / nrows.max() + (1.0 - sh)

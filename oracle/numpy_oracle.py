@@ -489,7 +489,8 @@ def _pair_worker(job):
     return times, timers.get("kernel_eval", 0.0), timers.get("dgemm_proj", 0.0)
 
 
-def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=2048, target_seconds=20.0, workers=None):
+def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=2048, target_seconds=20.0, workers=None, pool=None,
+                        probe_seconds=None):
     """Time the lean CPU path of predict3 on a bounded, deterministic sample and scale to the whole cube.
 
     Arrangement = the one that produced the full-size fixtures (tests/golden/make_fullsize_golden.py): the projection Pt = A.K is
@@ -501,6 +502,8 @@ def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=20
     variance are linear in the column count: timed on one panel with all BLAS threads and scaled by N / panel_cols.  The M x M
     Cholesky is timed in full on an SPD matrix of the true size.  When the whole inversion fits ``target_seconds`` it is run in
     full instead (single process, BLAS on all threads; ``sample`` says "full").
+    ``pool`` / ``probe_seconds``: a worker pool and the probe result of an earlier call (a caller that times many steps keeps
+    both, so that process start-up and the probe are paid once).
     Returns the estimated whole-cube seconds, the per-stage split and the sample description."""
     import multiprocessing as mp
     c, A_list, params, sig, w, amp, pts = _timing_operands(cfg, gp_length)
@@ -516,9 +519,12 @@ def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=20
     all_j = list(range(0, N, jchunk))
     n_panels = -(-N // panel_cols)
     # probe one pair (also warms the BLAS threads up; not part of the sample)
-    t0 = time.perf_counter()
-    pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=all_j[:1])
-    per = max(time.perf_counter() - t0, 1e-4)
+    if probe_seconds is None:
+        t0 = time.perf_counter()
+        pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=all_j[:1])
+        per = max(time.perf_counter() - t0, 1e-4)
+    else:
+        per = probe_seconds
     if per * len(all_j) * n_panels * 1.3 <= target_seconds:
         # ---- the whole inversion fits the budget: run it in full
         A_dense = [A[:, np.arange(N)] for A in A_list]
@@ -532,17 +538,20 @@ def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=20
                                 chol=timers["chol"], trsm=timers["trsm"], mean_var=timers["mean_var"]),
                     sample="full: the whole inversion in one process (%d panels of %d voxel columns x %d contraction chunks, AkA, Cholesky "
                            "M=%d, triangular solve, mean + variance)" % (n_panels, panel_cols, len(all_j), M),
-                    full=True, workers=1, pair_seconds=dict(median=per, min=per, max=per, n=0), checksum=float(np.nansum(mu) + np.nansum(var)))
+                    full=True, workers=1, probe_seconds=per, pair_seconds=dict(median=per, min=per, max=per, n=0),
+                    checksum=float(np.nansum(mu) + np.nansum(var)))
     # ---- bounded sample: `workers` processes x n pairs each (under contention a pair is slower than the probe: allow for 2x)
-    n_each = int(max(2, min(len(all_j), 0.5 * target_seconds / (2.0 * per))))
+    n_each = int(max(1, min(len(all_j), 0.5 * target_seconds / (2.0 * per))))
     jobs = []
     for wk in range(workers):
         sel = [all_j[(wk * n_each + i) % len(all_j)] for i in range(n_each)]
         jobs.append((dict(cfg), None if gp_length is None else list(map(float, gp_length)), didx.tolist(), cols, jchunk, sel))
     t0 = time.perf_counter()
-    if workers > 1:
-        with mp.get_context("spawn").Pool(workers) as pool:      # spawn: the caller may hold a CUDA context, which must not be forked
-            res = pool.map(_pair_worker, jobs, chunksize=1)
+    if pool is not None:
+        res = pool.map(_pair_worker, jobs, chunksize=1)
+    elif workers > 1:
+        with mp.get_context("spawn").Pool(workers) as own:       # spawn: the caller may hold a CUDA context, which must not be forked
+            res = own.map(_pair_worker, jobs, chunksize=1)
     else:
         res = [_pair_worker(jobs[0])]
     t_wall = time.perf_counter() - t0
@@ -583,7 +592,7 @@ def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=20
                        "pairs with all %d sensor rows, each pair timed; aggregate %.2f pairs/s scaled to the cube's %.0f pairs; AkA / triangular "
                        "solve / mean+variance timed on one panel with BLAS on all threads, scaled x%.1f; Cholesky M=%d timed in full"
                        % (workers, n_each, panel_cols, jchunk, 2 * Ns, rate, n_pairs, scale_cols, M),
-                full=False, workers=workers,
+                full=False, workers=workers, probe_seconds=per,
                 pair_seconds=dict(median=float(np.median(pair_t)), min=float(pair_t.min()), max=float(pair_t.max()), n=int(pair_t.size)),
                 checksum=float(np.nansum(mu) + np.nansum(var)))
 
