@@ -220,7 +220,17 @@ __global__ void table_extent_kernel(const uint8_t* __restrict__ t8, long ext, in
 }
 
 // voxel-column tile at position `pos` of task tq
-__device__ __forceinline__ int tile_at(const Params& P, int tq, int pos) { return P.perm ? P.perm[(long)tq * P.n_itile + pos] : pos; }
+// (rem = tile index inside the task = stile * n_itile + pos).  The sorted order runs from the most to the fewest K steps for even
+// sensor-row tiles and back for odd ones: a round of gridDim.x consecutive tiles that straddles two sensor-row tiles then holds
+// tiles of similar cost from both (n_itile is not a multiple of the grid size), instead of the cheapest of one and the dearest of
+// the next, which made every CTA of that round wait for the dear ones.
+__device__ __forceinline__ int tile_at(const Params& P, int tq, long rem) {
+    const int stile = (int)(rem / P.n_itile);
+    int pos = (int)(rem - (long)stile * P.n_itile);
+    if (!P.perm) return pos;
+    if (stile & 1) pos = P.n_itile - 1 - pos;
+    return P.perm[(long)tq * P.n_itile + pos];
+}
 
 // keys[tq][i] = K steps of voxel-column tile i in task tq
 __global__ void tile_steps_kernel(const Params P, int ksteps, int* __restrict__ keys) {
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int tq = (int)(tile / tiles_per_task);
             const int task = (tq / P.nr) * 3 + tq % P.nr;             // c * 3 + r
-            const int itile = tile_at(P, tq, (int)((tile % tiles_per_task) % P.n_itile));
+            const int itile = tile_at(P, tq, tile % tiles_per_task);
             const KRange kr = tile_krange(P, task, itile, ksteps);
             const int nt = (int)kr.nt;
             const int i0 = itile * 128 + 32 * q4 + (lane & 16);       // first voxel column of this half-warp's segment
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
                 const int tq = (int)(tile / tiles_per_task);
                 const int stile = (int)((tile % tiles_per_task) / P.n_itile);
                 const uint8_t* src = P.a8[tq / P.nr] + (size_t)stile * ksteps * B_BYTES;
-                const KRange kr = tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, tile_at(P, tq, (int)((tile % tiles_per_task) % P.n_itile)), ksteps);
+                const KRange kr = tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, tile_at(P, tq, tile % tiles_per_task), ksteps);
                 if (P.steps_ctr) atomicAdd(P.steps_ctr, (unsigned long long)kr.nt);
                 for (int jj = 0; jj < kr.nrows; ++jj) {
                     const uint8_t* rowsrc = src + (size_t)((kr.jya + jj) * kr.rowsteps + kr.koff - P.ks_base) * B_BYTES;
@@ -433,7 +443,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
             uint64_t* db = done_bar;
             for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int tq = (int)(tile / tiles_per_task);
-                const int nt = (int)tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, tile_at(P, tq, (int)((tile % tiles_per_task) % P.n_itile)), ksteps).nt;
+                const int nt = (int)tile_krange(P, (tq / P.nr) * 3 + tq % P.nr, tile_at(P, tq, tile % tiles_per_task), ksteps).nt;
                 for (int k0 = 0; k0 < nt; k0 += chunk_steps, ++chunk_id) {
                     const int k1 = min(nt, k0 + chunk_steps);
                     mbar_wait(&tempty_bar, (chunk_id & 1) ^ 1);     // epilogue has drained the accumulators
@@ -471,7 +481,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) ozaki_project_kernel(const __gr
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int tq = (int)(tile / tiles_per_task);
             const long rem = tile % tiles_per_task;
-            const int stile = (int)(rem / P.n_itile), itile = tile_at(P, tq, (int)(rem % P.n_itile));
+            const int stile = (int)(rem / P.n_itile), itile = tile_at(P, tq, rem);
             const int c = tq / P.nr, r = tq % P.nr, task = c * 3 + r;
             const int s0 = stile * NT, i = itile * 128 + m;
             const bool col_ok = i < P.ncol;
