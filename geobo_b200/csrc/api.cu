@@ -914,9 +914,10 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
         oa.n[0] = (int)p->n[0]; oa.n[1] = (int)p->n[1]; oa.n[2] = (int)p->n[2];
         // tile-round pacing (default on; GEOBO_B200_TILE_SYNC=0: free-running CTAs)
         // GEOBO_B200_TILE_SYNC: 0 = free-running CTAs, 1 = all CTAs start a round together, n > 1 = a CTA may run n - 1 rounds ahead.
-        // Default 2 (measured on the 64x64x32 and 32^3 cubes, profiles/r2_bench_f_*.json: one round of slack absorbs what the sorted
-        // tile order leaves of the edge-tile imbalance and keeps the HBM traffic of the launch near the strict setting's)
-        int pace_mode = 2;
+        // Default (measured, profiles/r2_bench_n_*.json): strict when a sensor-row tile spans several rounds (>= 4 x SM count
+        // voxel-column tiles: 64x64x32 on one GPU -- 42.8 k vs 41.5 k voxels/s, and the lowest HBM traffic), else one round of
+        // slack (32^3, multi-GPU shards: few rounds per sensor-row tile, the round boundaries weigh more -- 911 k vs 875 k at 32^3)
+        int pace_mode = ((ncol + 127) / 128 >= 4L * ctx->sm_count) ? 1 : 2;
         if (const char* ev = getenv("GEOBO_B200_TILE_SYNC")) pace_mode = atoi(ev);
         const bool pace = pace_mode > 0;
         oa.sync_slack = pace_mode > 1 ? pace_mode - 1 : 0;
