@@ -194,11 +194,27 @@ class Inversion:
         world, rk = _dist.world_size(), _dist.rank()
         self._bounds = self.shard_bounds() if world > 1 else [(0, N)]
         c0, c1 = self._bounds[rk]
+        # The device problem (sensitivity matrices, their digit blocks, every workspace) depends only on the geometry: a repeated
+        # cubing() on the same cube, sensors and drilled voxels -- new survey data, new hyper-parameters -- keeps it and only
+        # uploads the new data vector instead of recomputing A_sens and re-slicing its digits.
+        import hashlib
+        hsh = hashlib.blake2b(digest_size=16)
+        for a in (np.ascontiguousarray(self.Edges, dtype=float), np.ascontiguousarray(loc[:nsens]), np.ascontiguousarray(self._drill_idx, dtype=np.int64),
+                  np.ascontiguousarray(_cfg.magneticField, dtype=float)):
+            hsh.update(a.tobytes())
+        key = (xN, yN, zN, float(_cfg.xvoxsize), float(_cfg.yvoxsize), float(_cfg.zvoxsize), float(_cfg.c_MILLIGALS_UNITS), float(_cfg.fcor_grav),
+               float(_cfg.fcor_mag), c0, c1, id(ctx), hsh.hexdigest())
+        if self._problem is not None and getattr(self._problem, "h", None) and getattr(self, "_problem_key", None) == key:
+            self._problem.set_data(self.Fs3)
+            self._lazy = {}
+            return
         if self._problem is not None:
             self._problem.close()
         self._problem = _lib.Problem(ctx, (xN, yN, zN), (_cfg.xvoxsize, _cfg.yvoxsize, _cfg.zvoxsize), self.Edges,
                                      loc[:nsens], _cfg.magneticField, _cfg.c_MILLIGALS_UNITS, _cfg.fcor_grav, 1.0,
                                      _cfg.fcor_mag, self._drill_idx, c0, c1)
+        self._problem_key = key
+        self._problem_builds = getattr(self, "_problem_builds", 0) + 1
         self._problem.set_data(self.Fs3)
         self._lazy = {}
 

@@ -271,6 +271,33 @@ def test_non_finite_covariance_without_drill_data_exits_like_reference(ctx, caps
     assert "Cholesky decompostion failed" in capsys.readouterr().out
 
 
+def test_repeated_cubing_reuses_the_device_problem_of_the_same_geometry(ctx):
+    """A second cubing() on the same Inversion with the same cube / sensors / drilled voxels keeps the device problem (sensitivities,
+    workspaces) and only uploads the new data; other drilled voxels rebuild it.  Either way the cubes equal a fresh instance's."""
+    c = configure(base_cfg(), xNcube=7, yNcube=5, zNcube=3, kernelfunc="exp")
+    f = synthetic_inputs(c, 3)
+    inv, out1 = run_cubing(f)
+    assert inv._problem_builds == 1
+    g = dict(f, grav=f["grav"] * 1.5 + 0.1 * np.arange(f["grav"].size), mag=f["mag"][::-1].copy())
+    out2 = inv.cubing(g["grav"], g["mag"], g["drillfield"], g["sensor_locations"], g["drilldata0"])
+    assert inv._problem_builds == 1                                     # same device problem
+    _, fresh = run_cubing(g)
+    for n, a, b in zip(CUBES, out2, fresh):
+        assert np.array_equal(a, b), n
+    ref, _ = o.cubing_lean(c, g["grav"], g["mag"], g["drillfield"], g["sensor_locations"], g["drilldata0"])
+    for n, a, r in zip(CUBES, out2, ref):
+        assert normwise_err(a, r) < TOL_CUBE, n
+    d0 = f["drilldata0"].copy().ravel()
+    idx = np.flatnonzero(d0)
+    d0[(idx[0] + 1) % d0.size], d0[idx[0]] = d0[idx[0]], 0.0            # another voxel drilled: another A_drill
+    d0 = d0.reshape(f["drilldata0"].shape)
+    out3 = inv.cubing(f["grav"], f["mag"], d0[d0 != 0], f["sensor_locations"], d0)
+    assert inv._problem_builds == 2
+    ref3, _ = o.cubing_lean(c, f["grav"], f["mag"], d0[d0 != 0], f["sensor_locations"], d0)
+    for n, a, r in zip(CUBES, out3, ref3):
+        assert normwise_err(a, r) < TOL_CUBE, n
+
+
 def test_calc_logl_vs_oracle(ctx):
     c = configure(base_cfg(), xNcube=6, yNcube=5, zNcube=4, kernelfunc="exp")
     f = synthetic_inputs(c, 4)
