@@ -348,6 +348,38 @@ cudaError_t chol_factor(double* Bm, long ldb, int Mp, int Mtrue, const CholWork&
         if ((e = cudaStreamWaitEvent(s, la.b_done, 0)) != cudaSuccess) return e;
         la.b_pending = false;
     }
+    // PROFILING AID (GEOBO_B200_CHOL_EMULATE="nranks,rank", off by default): after the factorisation, launch once more the trailing
+    // updates that rank `rank` of `nranks` issues in chol_factor_dist (block-cyclic column blocks, one batched K = outer x 128 launch
+    // per outer block, operands from the finished factor) into a scratch matrix, so that `ncu` -- which cannot be attached to a
+    // multi-rank job on this pool -- can capture the kernel with exactly the grid and operand shapes of an 8-GPU run on ONE GPU.
+    // The results of these launches are discarded.
+    if (const char* ev = getenv("GEOBO_B200_CHOL_EMULATE")) {
+        int nr = 0, me = 0;
+        if (sscanf(ev, "%d,%d", &nr, &me) == 2 && nr > 1 && me >= 0 && me < nr && outer > 1) {
+            double* scratch = nullptr;
+            if ((e = cudaMalloc(&scratch, (size_t)Mp * ldb * sizeof(double))) != cudaSuccess) return e;
+            cudaMemsetAsync(scratch, 0, (size_t)Mp * ldb * sizeof(double), s);
+            for (int ob = 0; ob < nblk; ob += outer) {
+                const int o0 = ob * NB, oe = (ob + outer < nblk ? ob + outer : nblk), o1 = oe * NB;
+                gemm::TaskBatch b2;
+                b2.n = 0;
+                for (int jb = oe; jb < nblk; ++jb) {
+                    if (jb % nr != me) continue;
+                    const int j0 = jb * NB;
+                    const double* lj = Bm + (long)j0 * ldb + o0;
+                    double* c = scratch + (long)j0 * ldb + j0;
+                    b2.t[b2.n++] = make_task(lj, ldb, lj, ldb, c, ldb, c, ldb, Mp - j0, NB, o1 - o0, -1.0, 1.0, 0);
+                    if (b2.n == gemm::MAX_TASKS) {
+                        if ((e = gemm::launch(b2, gemm::B_T, s)) != cudaSuccess) { cudaFree(scratch); return e; }
+                        b2.n = 0;
+                    }
+                }
+                if (b2.n && (e = gemm::launch(b2, gemm::B_T, s)) != cudaSuccess) { cudaFree(scratch); return e; }
+            }
+            cudaStreamSynchronize(s);
+            cudaFree(scratch);
+        }
+    }
     return cudaSuccess;
 }
 
