@@ -172,7 +172,10 @@ typedef struct gb_hyper {
 } gb_hyper;
 
 /* Builds the device-resident problem: computes both sensitivity matrices on the GPU
- * (Inversion.cubing, inversion.py:216-230, without materialising the zero-padded Asens3). */
+ * (Inversion.cubing, inversion.py:216-230, without materialising the zero-padded Asens3).
+ * Lean mode: when the two fp64 matrices would take more than a fifth of the device memory (96x96x48 and up; GEOBO_B200_LEAN_A=1/0
+ * forces it) they are NOT kept: only their int8 digit blocks are, and every fp64 pass over them regenerates them chunk by chunk.
+ * Such a problem only runs the int8 paths (gb_hyper.slices = 4, 5, 6); slices = 0 is refused with GB_ERR_UNSUPPORTED. */
 int gb_problem_create(gb_ctx* ctx, const gb_problem_desc* desc, gb_problem** out);
 int gb_problem_destroy(gb_problem* p);
 /* Fs3 = normalised [grav, mag, drill] data vector, length M = 2*nsens + ndrill (inversion.py:221). */
@@ -180,7 +183,10 @@ int gb_problem_set_data(gb_problem* p, const double* fs3);
 /* Inversion.predict3 (inversion.py:77-122) without the 3N x 3N covariance:
  * mu and var = diag(cov) are returned for this rank's voxel-column shard as [3][col_end - col_begin]
  * (property-major; the whole 3N vector on one GPU); logl and info are identical on every rank.
- * mu / var / logl may be NULL (results stay on the device).  Returns info (>0) if AkA is not PD. */
+ * mu / var / logl may be NULL (results stay on the device).  Returns info (>0) if AkA is not PD -- also when a covariance value is
+ * not finite (e.g. matern32 with equal length scales), which makes the reference's Cholesky raise (inversion.py:98-104).
+ * With ndrill == 0 the third property block of mu / var is NOT computed and returned as NaN: the reference multiplies it by the std
+ * of an empty array (inversion.py:213-214), so its drill cubes are NaN as well. */
 int gb_predict(gb_problem* p, const gb_hyper* h, int flags, double* mu, double* var, double* logl, int* info);
 /* Inversion.calc_logl (inversion.py:125-152): returns -logl without the N log(2 pi) term; +inf if not PD. */
 int gb_neg_logl(gb_problem* p, const gb_hyper* h, double* neg_logl, int* info);
