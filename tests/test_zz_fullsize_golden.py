@@ -125,5 +125,5 @@ def test_fullsize_cubing_vs_cpu_oracle(name, prec):
         pass
     worst = max(v for k, v in errs.items() if k != "logl_rel")
     assert worst < TOL_STATED, errs
-    assert errs["logl_rel"] < (1e-6 if prec == "fp64" else 1e-4), errs
+    assert errs["logl_rel"] < 1e-6, errs          # measured: fp64 <= 7e-12, int8x5 <= 7.7e-8
     assert np.allclose(inv.gp_length, g["gl_after"])
