@@ -495,7 +495,7 @@ def ctx_device():
     return int(os.environ.get("GEOBO_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
 
 
-def cpu_baseline(args, cfg, wl, f, y, target_seconds=20.0, pool=None, probe_seconds=None):
+def cpu_baseline(args, cfg, wl, f, y, target_seconds=20.0, pool=None, probe_seconds=None, state=None):
     """Lean NumPy/SciPy restatement of the reference (oracle/numpy_oracle.py) on this box's host cores: the projection in one
     worker process per core (the arrangement of the full-size fixture runs), the other stages with BLAS on all threads."""
     from oracle import numpy_oracle as o
@@ -507,7 +507,7 @@ def cpu_baseline(args, cfg, wl, f, y, target_seconds=20.0, pool=None, probe_seco
     # the sensitivities only enter the timed stages as dgemm operands (timing is value-independent): the oracle's A_sens for a
     # few sensors, tiled (oracle.TiledSens) -- the bounded sample does not spend minutes in the (untimed) A_sens loop
     res = o.cpu_baseline_sample(cfg, didx, np.nan_to_num(y), gp_length=gl.copy(), target_seconds=target_seconds, workers=threads, pool=pool,
-                                probe_seconds=probe_seconds)
+                                probe_seconds=probe_seconds, state=state)
     out = {"value": N / res["seconds_estimated"], "unit": "voxels/s", "cores": int(threads), "kind": "port",
            "host_cpus": os.cpu_count(), "sample": res["sample"], "full_inversion": bool(res["full"]),
            "seconds_estimated_full": res["seconds_estimated"], "seconds_measured": res["seconds_measured"], "stages_s": res["stages"],
@@ -559,10 +559,11 @@ def run_reference(args):
     vals, last = [], None
     import multiprocessing as mp
     # one worker pool and one probe for all steps (process start-up is not part of a step)
+    state = {}
     with mp.get_context("spawn").Pool(cpu_threads()) as pool:
         for i in range(args.warmup + args.steps):
             last = cpu_baseline(args, cfg, wl, f, y, target_seconds=per_step_budget, pool=pool,
-                                probe_seconds=None if last is None else last["probe_seconds"])
+                                probe_seconds=None if last is None else last["probe_seconds"], state=state)
             if i >= args.warmup:
                 vals.append(last["value"])
     value = float(np.mean(vals))

@@ -154,6 +154,16 @@ class Inversion:
         slices = self._slices()
         if world <= 1 or not slices or self._structure() != "dense":
             return _dist.shard_bounds(N, world)
+        # (memoised: the estimate costs a few small device calls with allocations, ~0.1 s next to tens of GB of live buffers)
+        nd_now = int(np.count_nonzero(np.asarray(self.drilldata0))) if hasattr(self, "drilldata0") else 0
+        key = (xN, yN, zN, world, slices, _cfg.kernelfunc, tuple(np.asarray(self.gp_length, dtype=float).tolist()), float(_cfg.yvoxsize), nd_now)
+        cache = self.__dict__.setdefault("_bounds_cache", {})
+        if key in cache:
+            return cache[key]
+        cache[key] = self._shard_bounds_weighted(xN, yN, zN, N, world, slices)
+        return cache[key]
+
+    def _shard_bounds_weighted(self, xN, yN, zN, N, world, slices):
         reach = self._culling_reach_rows(slices)
         iy = np.arange(yN)
         nrows = np.minimum(yN - 1, iy + reach) - np.maximum(0, iy - reach) + 1
@@ -165,15 +175,15 @@ class Inversion:
         Mp = -(-(2 * Ns + nd) // 128) * 128
         per_col = Mp * (3 if nd else 2) * 8.0 + 3.0 * slices * Ns         # Pt, shard digit blocks, row digits of one AkA block
         fixed = 2.0 * Mp * Mp * 8.0 + 20e9                                # AkA / L and Linv; digit scratch, chunk buffers, tables, NCCL
-        # what is free now (after context + NCCL set-up, incl. what the context's buffer cache would give back), with a margin:
-        # at 128x128x64 on 8 GPUs the first weighted split left 0.24 GB free on the edge ranks (profiles/r2_memlog_cfg5_dense_n8_rank0.txt)
-        info = _lib.default_context().device_info()
-        total = (0.9 * float(info["free_bytes"]) - 6e9) / 0.85
+        # The limit must be the SAME number on every rank (all ranks have to pick the same split), so it comes from the device's
+        # total memory, not from what happens to be free on this rank; 0.8 of it leaves room for context, NCCL and fragmentation
+        # (at 128x128x64 on 8 GPUs an early, laxer rule left 0.24 GB free on the edge ranks, profiles/r2_memlog_cfg5_dense_n8_rank0.txt).
+        total = float(_lib.default_context().device_info()["total_bytes"])
         bounds = _dist.shard_bounds(N, world)
         for sh in (share, 0.5 * share, 0.25 * share):
             w = sh * nrows / nrows.max() + (1.0 - sh)
             cand = _dist.shard_bounds(N, world, weights=w)
-            if max(c1 - c0 for c0, c1 in cand) * per_col + fixed < 0.85 * total:
+            if max(c1 - c0 for c0, c1 in cand) * per_col + fixed < 0.8 * total:
                 bounds = cand
                 break
         return bounds

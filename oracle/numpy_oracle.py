@@ -472,15 +472,28 @@ def _timing_operands(cfg, gp_length):
     return c, [Ag, Am], params, sig, w, amp, pts
 
 
+_WORKER_CACHE = {}
+
+
+def json_key(cfg):
+    import json
+    return json.dumps(cfg, sort_keys=True, default=str)
+
+
 def _pair_worker(job):
     """One worker process of the CPU timing sample: ``n`` (panel, chunk) pairs of the projection with ONE BLAS thread, like the
     workers of tests/golden/make_fullsize_golden.py.  Returns its per-pair times and kernel-evaluation / dgemm split."""
-    cfg, gp_length, didx, cols, jchunk, jstarts = job
+    cfg, gp_length, didx, cols, jchunk, jstarts, warm = job
     from threadpoolctl import threadpool_limits
     with threadpool_limits(1):
-        c, A_list, params, sig, w, amp, pts = _timing_operands(cfg, gp_length)
+        key = (json_key(cfg), None if gp_length is None else tuple(gp_length))
+        if _WORKER_CACHE.get("key") != key:                   # a pool that serves several steps builds its operands once
+            _WORKER_CACHE.clear()
+            _WORKER_CACHE.update(key=key, ops=_timing_operands(cfg, gp_length))
+        c, A_list, params, sig, w, amp, pts = _WORKER_CACHE["ops"]
         didx = np.asarray(didx, dtype=int)
-        pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=jstarts[:1])     # warm-up pair, not timed
+        if warm:
+            pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=jstarts[:1])     # warm-up pair, not timed
         timers, times = {}, []
         for j0 in jstarts:
             t0 = time.perf_counter()
@@ -490,7 +503,7 @@ def _pair_worker(job):
 
 
 def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=2048, target_seconds=20.0, workers=None, pool=None,
-                        probe_seconds=None):
+                        probe_seconds=None, state=None):
     """Time the lean CPU path of predict3 on a bounded, deterministic sample and scale to the whole cube.
 
     Arrangement = the one that produced the full-size fixtures (tests/golden/make_fullsize_golden.py): the projection Pt = A.K is
@@ -502,11 +515,15 @@ def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=20
     variance are linear in the column count: timed on one panel with all BLAS threads and scaled by N / panel_cols.  The M x M
     Cholesky is timed in full on an SPD matrix of the true size.  When the whole inversion fits ``target_seconds`` it is run in
     full instead (single process, BLAS on all threads; ``sample`` says "full").
-    ``pool`` / ``probe_seconds``: a worker pool and the probe result of an earlier call (a caller that times many steps keeps
-    both, so that process start-up and the probe are paid once).
+    ``pool`` / ``probe_seconds`` / ``state``: a worker pool, the probe result and a dict for the untimed preparations (operands,
+    the panel the small stages are timed on, "workers are warm") of an earlier call -- a caller that times many steps keeps them,
+    so that process start-up, the probe and the preparations are paid once and a step is the timed sample only.
     Returns the estimated whole-cube seconds, the per-stage split and the sample description."""
     import multiprocessing as mp
-    c, A_list, params, sig, w, amp, pts = _timing_operands(cfg, gp_length)
+    state = {} if state is None else state
+    if "ops" not in state:
+        state["ops"] = _timing_operands(cfg, gp_length)
+    c, A_list, params, sig, w, amp, pts = state["ops"]
     xN, yN, zN = c.xNcube, c.yNcube, c.zNcube
     N = xN * yN * zN
     Ns = xN * yN
@@ -545,7 +562,8 @@ def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=20
     jobs = []
     for wk in range(workers):
         sel = [all_j[(wk * n_each + i) % len(all_j)] for i in range(n_each)]
-        jobs.append((dict(cfg), None if gp_length is None else list(map(float, gp_length)), didx.tolist(), cols, jchunk, sel))
+        jobs.append((dict(cfg), None if gp_length is None else list(map(float, gp_length)), didx.tolist(), cols, jchunk, sel,
+                     not state.get("workers_warm", False)))
     t0 = time.perf_counter()
     if pool is not None:
         res = pool.map(_pair_worker, jobs, chunksize=1)
@@ -555,6 +573,8 @@ def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=20
     else:
         res = [_pair_worker(jobs[0])]
     t_wall = time.perf_counter() - t0
+    if pool is not None:
+        state["workers_warm"] = True
     pair_t = np.concatenate([np.asarray(r[0]) for r in res])
     rate = sum(len(r[0]) / sum(r[0]) for r in res)               # pairs per second, all workers together
     k_ev, k_mm = sum(r[1] for r in res), sum(r[2] for r in res)
@@ -563,7 +583,9 @@ def cpu_baseline_sample(cfg, didx, y, gp_length=None, panel_cols=2048, jchunk=20
     n_pairs = scale_cols * len(all_j)
     t_proj = n_pairs / rate
     # ---- the other stages on one panel, BLAS on all threads
-    Pt = pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=all_j[:2])      # operand for the timings below
+    if "Pt" not in state:
+        state["Pt"] = pt_panel(c, params, w, amp, A_list, didx, pts, cols, jchunk=jchunk, jstarts=all_j[:1])      # operand for the timings below
+    Pt = state["Pt"]
     t0 = time.perf_counter()
     AkA = np.empty((M, M))
     AkA[:Ns] = A_list[0][:, cols] @ Pt[:, 0, :].T
