@@ -37,3 +37,22 @@ def align_drill(coord, data, xxx=None, yyy=None, zzz=None, voxelsize=None, ctx=N
 
 
 align_drill2 = align_drill      # utils.py:55-83 differs only in how it tests for an empty selection
+
+
+def downsample_survey(grav_img, mag_img):
+    """The survey part of ``read_surveydata`` after the GeoTIFF read (``run_geobo.py:53-65``): both survey maps resampled to one
+    value per voxel column with ``scipy.ndimage.zoom`` (factor ``xNcube / image width``, the reference's call with its defaults:
+    cubic spline, prefiltered) and the sensor coordinates over the voxel-column centres at height ``zmax + zoff``.
+
+    Host code on purpose: O(Ns) work on two 2-D images, done once per settings file; the identical library call keeps the result
+    bit-identical to the reference's.  Returns ``(grav.flatten(), mag.flatten(), sensor_locations)`` -- the first, second and
+    fourth argument of ``Inversion.cubing``."""
+    from scipy.ndimage import zoom
+    from .synth import sensor_grid
+    out = []
+    for img in (np.asarray(grav_img), np.asarray(mag_img)):
+        img2 = zoom(img, _cfg.xNcube * 1. / img.shape[1])
+        if img2.shape != (_cfg.yNcube, _cfg.xNcube):
+            raise AssertionError("zoomed survey has shape %r, expected (yNcube, xNcube) = %r" % (img2.shape, (_cfg.yNcube, _cfg.xNcube)))
+        out.append(img2.flatten())
+    return out[0], out[1], sensor_grid()

@@ -80,6 +80,17 @@ def test_geometry_matches_reference_fixture():
     assert np.allclose(inv.gp_length, 2 * 3050 / 8)       # Q6: xvoxsize for all three
 
 
+def test_downsample_survey_matches_the_reference_driver():
+    """tests/golden/survey_zoom.npz: the raw survey images of the reference's example 2 (61 x 39 GeoTIFFs) and what its own
+    read_surveydata handed to Inversion.cubing (the `grav`, `mag`, `sensor_locations` of example2.npz, captured from the
+    unmodified driver)."""
+    from geobo_b200 import config_loader as cl, utils
+    g = load_golden("survey_zoom.npz")
+    cl.load_settings(json.loads(str(g["cfg"])), make_outpath=False)
+    grav, mag, loc = utils.downsample_survey(g["grav_img"], g["mag_img"])
+    assert np.array_equal(grav, g["grav"]) and np.array_equal(mag, g["mag"]) and np.array_equal(loc, g["sensor_locations"])
+
+
 def test_shard_columns_partition():
     from geobo_b200.dist import shard_columns
     for n, world in [(6400, 1), (6400, 2), (32768, 8), (442368, 8), (1000, 3), (131072, 4)]:
