@@ -134,6 +134,11 @@ def _worker(rank, world, port, q):
     c0, c1 = dist.shard_columns(n, world, rank)
     full_truth = np.arange(3 * n, dtype=float).reshape(3, n)
     got = dist.allgather_columns(full_truth[:, c0:c1], n)
+    # unequal (work-balanced) shards: the gather pads to the largest one
+    wb = dist.shard_bounds(n, world, weights=[1.0, 1.0, 1.0, 3.0, 3.0, 3.0, 3.0, 3.0])
+    assert wb[0][1] - wb[0][0] != wb[1][1] - wb[1][0]
+    got_w = dist.allgather_columns(full_truth[:, wb[rank][0]:wb[rank][1]], n, bounds=wb)
+    assert np.array_equal(got_w, full_truth)
     mx = dist.max_over_ranks(10.0 + rank)
     uid = dist.broadcast_bytes(b"id-from-rank-0" if rank == 0 else None)
     dist.barrier()
