@@ -791,7 +791,7 @@ static int run_predict(gb_problem* p, const gb_hyper* h, bool full, bool all_blo
                            "(got zNcube=%lld, columns=%ld); use slices = 0", (long long)p->n[2], ncol);
         // scope of the digit blocks: the dense projection contracts over all N columns; with a structured projection on a lean
         // problem they are only the N side of the AkA products, i.e. this rank's voxel columns (128x128x64: 21 GB instead of 172)
-        if (p->lean && !structured && p->a8_slices != S) {
+        if (p->lean && !structured && (p->a8_slices != S || p->a8_scope != 1)) {      // (also when a structured run left shard-only blocks)
             size_t fr = 0, tot = 0;
             GB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
             p->stream_a8 = 2 * (size_t)ozaki_rows_bytes(Ns, p->Kp, S, ozaki_tile_np(S)) > tot / 4;
