@@ -91,3 +91,72 @@ def test_every_skipped_k_step_holds_only_zero_digits(shape, kernel, gl_mult, S):
                     oz = vz[i][None, :] - vz[j][:, None] + (zN - 1)
                     assert not nzmask[oy, ox, oz].any(), (kernel, cb, r, itile)
     assert culled_any or kernel == "matern32"          # the compact and the short exp kernels really cull on these cubes
+
+
+def tile_krange_chunk(xN, yN, zN, c0, ncol, itile, ey, ex, cy0, cy1):
+    """tile_krange with the streamed-contraction clamp (rows [cy0, cy1) of one launch): None when the tile has no step in the chunk."""
+    XZ = xN * zN
+    g0 = c0 + itile * 128
+    g1 = min(g0 + 127, c0 + ncol - 1)
+    iya, iyb = g0 // XZ, g1 // XZ
+    ixa, ixb = 0, xN - 1
+    if iya == iyb:
+        ixa, ixb = (g0 % XZ) // zN, (g1 % XZ) // zN
+    jya, jyb = max(0, iya - ey), min(yN - 1, iyb + ey)
+    jya, jyb = max(jya, cy0), min(jyb, cy1 - 1)
+    if jyb < jya:
+        return None
+    jxa, jxb = max(0, ixa - ex), min(xN - 1, ixb + ex)
+    koff = (jxa * zN) // 32
+    return jya, jyb - jya + 1, koff, ((jxb + 1) * zN + 31) // 32 - koff, XZ // 32
+
+
+@pytest.mark.parametrize("chunk_rows", [1, 2, 3, 5])
+def test_streamed_chunks_partition_the_kept_steps(chunk_rows):
+    """Streamed contraction: one launch per chunk of voxel rows; the steps a tile visits over all launches are exactly the steps of
+    the unchunked launch, each once (the launches add into Pt)."""
+    xN, yN, zN, ey, ex = 8, 11, 16, 3, 2
+    N = xN * yN * zN
+    for c0, ncol in ((0, N), (512, N - 512)):
+        for itile in range((ncol + 127) // 128):
+            jya, nrows, koff, w, rowsteps = tile_krange(xN, yN, zN, c0, ncol, itile, ey, ex)
+            full = np.zeros(N // 32, dtype=int)
+            for jj in range(nrows):
+                full[(jya + jj) * rowsteps + koff:(jya + jj) * rowsteps + koff + w] += 1
+            acc = np.zeros(N // 32, dtype=int)
+            for y0 in range(0, yN, chunk_rows):
+                y1 = min(yN, y0 + chunk_rows)
+                kr = tile_krange_chunk(xN, yN, zN, c0, ncol, itile, ey, ex, y0, y1)
+                if kr is None:
+                    continue
+                a, n, ko, ww, rs = kr
+                ks_base, ksteps_local = y0 * rs, (y1 - y0) * rs
+                for jj in range(n):
+                    lo = (a + jj) * rs + ko
+                    assert ks_base <= lo and lo + ww <= ks_base + ksteps_local          # inside the chunk's digit blocks
+                    acc[lo:lo + ww] += 1
+            assert np.array_equal(acc, full) and full.max() == 1
+
+
+def test_alternating_sorted_tile_order_is_a_permutation_with_smooth_round_boundaries():
+    """tile_at: position -> voxel-column tile through the order sorted by K-step count, descending for even sensor-row tiles and
+    ascending for odd ones: every tile once per sensor-row tile, and consecutive positions across a sensor-row-tile boundary hold tiles
+    of equal cost."""
+    rng = np.random.default_rng(0)
+    n_itile, n_stile = 37, 5
+    keys = rng.integers(10, 60, n_itile)
+    rank = np.array([np.sum((keys > keys[i]) | ((keys == keys[i]) & (np.arange(n_itile) < i))) for i in range(n_itile)])   # tile_rank_kernel
+    perm = np.empty(n_itile, dtype=int)
+    perm[rank] = np.arange(n_itile)
+    assert sorted(perm) == list(range(n_itile)) and (np.diff(keys[perm]) <= 0).all()
+    seq = []
+    for rem in range(n_stile * n_itile):                       # tile_at
+        stile, pos = divmod(rem, n_itile)
+        if stile & 1:
+            pos = n_itile - 1 - pos
+        seq.append((stile, perm[pos]))
+    for st in range(n_stile):
+        assert sorted(t for s_, t in seq if s_ == st) == list(range(n_itile))
+    cost = np.array([keys[t] for _, t in seq])
+    for st in range(1, n_stile):
+        assert cost[st * n_itile - 1] == cost[st * n_itile]     # the same tile cost on both sides of the boundary
